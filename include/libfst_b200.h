@@ -1,0 +1,192 @@
+/* libfst_b200 — B200-native batched compose + shortest-path engine.
+ *
+ * C ABI of libfst_b200.so.  Two groups of entry points:
+ *
+ *  (1) DROP-IN SUBSET of the reference's C ABI (ontypehq/libfst include/fst.h):
+ *      the calls a client needs to build/load a transducer, compile a string,
+ *      run fst_compose_frozen_shortest_path and read the result.  Names,
+ *      argument meaning, return conventions and error behaviour are the
+ *      reference's; each declaration cites the reference line it replaces.
+ *      The search itself runs on the GPU (no CPU fallback: if no CUDA device is
+ *      usable the call fails with FST_INVALID_HANDLE).
+ *
+ *  (2) NEW batched entry points (not in the reference): many independent byte
+ *      strings against one frozen transducer in one call, host buffers or
+ *      device-resident buffers.
+ *
+ * Everything else in the reference's header (determinize, minimize, union, …)
+ * is grammar construction and stays with the Zig library; it is not exported.
+ */
+#ifndef LIBFST_B200_H
+#define LIBFST_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ── shared types: reference include/fst.h:28-60 ─────────────────────────── */
+typedef uint64_t FstMutableHandle; /* fst.h:30  generation<<32 | slot */
+typedef uint64_t FstHandle;        /* fst.h:31 */
+
+typedef enum {                     /* fst.h:34-40 */
+  FST_OK = 0,
+  FST_OOM = 1,
+  FST_INVALID_ARG = 2,
+  FST_INVALID_STATE = 3,
+  FST_IO_ERROR = 4
+} FstError;
+
+typedef struct {                   /* fst.h:50-55 (24 bytes) */
+  uint32_t ilabel;
+  uint32_t olabel;
+  double weight;
+  uint32_t nextstate;
+} FstArc;
+
+#define FST_NO_STATE UINT32_MAX        /* fst.h:58 */
+#define FST_EPSILON 0                  /* fst.h:59 */
+#define FST_INVALID_HANDLE UINT64_MAX  /* fst.h:60 */
+
+/* ── (1) drop-in subset ──────────────────────────────────────────────────── */
+
+/* mutable lifecycle + builders: fst.h:63-71, src/c-api.zig:436-505 */
+FstMutableHandle fst_mutable_new(void);
+FstMutableHandle fst_mutable_clone(FstMutableHandle handle);
+void fst_mutable_free(FstMutableHandle handle);
+uint32_t fst_mutable_add_state(FstMutableHandle handle);
+FstError fst_mutable_set_start(FstMutableHandle handle, uint32_t state);
+FstError fst_mutable_set_final(FstMutableHandle handle, uint32_t state, double weight);
+FstError fst_mutable_add_arc(FstMutableHandle handle, uint32_t src, uint32_t ilabel, uint32_t olabel,
+                             double weight, uint32_t nextstate);
+
+/* mutable queries (read the result chain): fst.h:74-79, src/c-api.zig:1376-1424 */
+uint32_t fst_mutable_start(FstMutableHandle handle);
+uint32_t fst_mutable_num_states(FstMutableHandle handle);
+uint32_t fst_mutable_num_arcs(FstMutableHandle handle, uint32_t state);
+double fst_mutable_final_weight(FstMutableHandle handle, uint32_t state);
+uint32_t fst_mutable_get_arcs(FstMutableHandle handle, uint32_t state, FstArc* buf, uint32_t buf_len);
+
+/* freeze: fst.h:82, src/c-api.zig:507-526 (sorts a snapshot by
+ * (ilabel, olabel, weight, nextstate), src/arc.zig:46-54) */
+FstHandle fst_freeze(FstMutableHandle mutable_handle);
+
+/* frozen lifecycle + queries: fst.h:85-91, src/c-api.zig:530-583.
+ * fst_free on a transducer that is pinned by a running search defers the
+ * destruction (and the release of its device image) to the last unpin. */
+void fst_free(FstHandle handle);
+uint32_t fst_start(FstHandle handle);
+uint32_t fst_num_states(FstHandle handle);
+uint32_t fst_num_arcs(FstHandle handle, uint32_t state);
+double fst_final_weight(FstHandle handle, uint32_t state);
+uint32_t fst_get_arcs(FstHandle handle, uint32_t state, FstArc* buf, uint32_t buf_len);
+
+/* native binary image: fst.h:96,99, src/c-api.zig:601-639, src/io/binary.zig:9-36,
+ * validation rules of src/fst.zig:227-273 (+ NaN weights rejected). */
+FstHandle fst_load(const char* path);
+FstError fst_save(FstHandle handle, const char* path);
+
+/* THE HOT PATH: fst.h:105-106, src/c-api.zig:744-811,
+ * src/ops/compose-shortest-path.zig:26-401.
+ * Returns a new mutable handle holding the best path as a linear chain
+ * (k+1 states, arc i = (ilabel, olabel, w1 (x) w2, i+1), final weight on state k);
+ * an empty FST when there is no path / n == 0 / a start state is missing;
+ * FST_INVALID_HANDLE for bad handles, n > 1, or any failure.
+ * `a` and `b` are not consumed.  The search runs on the current CUDA device. */
+FstMutableHandle fst_compose_frozen_shortest_path(FstMutableHandle a, FstHandle b, uint32_t n);
+
+/* string helpers: fst.h:131-133, src/c-api.zig:1334-1372, src/string.zig:24-97
+ * (label = byte + 1; print returns -1 if not a linear chain or buf too small). */
+FstMutableHandle fst_compile_string(const uint8_t* input, uint32_t len);
+int32_t fst_print_string(FstMutableHandle handle, uint8_t* buf, uint32_t buf_len);
+int32_t fst_print_output_string(FstMutableHandle handle, uint8_t* buf, uint32_t buf_len);
+
+/* fst.h:136, src/c-api.zig:295-329 — also releases all device memory. */
+void fst_teardown(void);
+
+/* ── (2) batched entry points (new) ──────────────────────────────────────── */
+
+/* Per-string status of a batched search. */
+typedef enum {
+  FST_B200_PATH = 0,        /* a best path was found (possibly of length 0)            */
+  FST_B200_NO_PATH = 1,     /* reference would return an empty FST                       */
+  FST_B200_CYCLE = 2,       /* reference hazard: back-pointer cycle through zero-weight
+                               epsilon loops (the reference runs out of memory here and
+                               returns FST_INVALID_HANDLE); reported, never emitted      */
+  FST_B200_TOO_LARGE = 3    /* search state does not fit the configured device budget    */
+} FstB200Status;
+
+/* Result of one batched call; all arrays are owned by the library and live in
+ * pinned host memory until fst_b200_batch_free. Semantics per string i are those
+ * of fst_compile_string(bytes_i) -> fst_compose_frozen_shortest_path(., b, 1). */
+typedef struct {
+  uint32_t n_strings;
+  const int32_t* status;         /* [n] FstB200Status                                    */
+  const uint64_t* path_offsets;  /* [n+1] arcs of string i are [off[i], off[i+1])         */
+  const uint32_t* ilabels;       /* [off[n]]                                             */
+  const uint32_t* olabels;       /* [off[n]]                                             */
+  const double* weights;         /* [off[n]] per-arc weight w1 (x) w2                     */
+  const double* final_weights;   /* [n] final weight of the chain's last state (+inf if none) */
+  const uint32_t* n_tuples;      /* [n] compose tuples the search created (work counter) */
+  const uint64_t* out_offsets;   /* [n+1] output-tape bytes of string i (epsilons dropped,
+                                    label-1), i.e. fst_print_output_string of the chain    */
+  const uint8_t* out_bytes;      /* [out_offsets[n]]                                     */
+  double device_ms;              /* device time of the search+emit kernels (CUDA events) */
+  uint64_t total_tuples;         /* sum of n_tuples                                      */
+  uint64_t total_relax;          /* relaxations performed (== composed arcs)             */
+  uint32_t launches;             /* kernels launched by this call                        */
+  uint32_t passes;               /* 1 + number of retry passes for oversized strings     */
+} FstB200BatchResult;
+
+/* Host-buffer batch: `bytes` holds the concatenated strings, string i is
+ * bytes[offsets[i] .. offsets[i+1]).  Copies inputs H2D, searches on the current
+ * CUDA device, copies results D2H.  Returns FST_INVALID_ARG for a bad handle or
+ * null pointers, FST_OOM on allocation failure, FST_INVALID_STATE if no CUDA
+ * device / kernel failure.  *out is set to NULL on error. */
+FstError fst_compose_frozen_shortest_path_batch(FstHandle b, const uint8_t* bytes, const uint64_t* offsets,
+                                                uint32_t n_strings, FstB200BatchResult** out);
+void fst_b200_batch_free(FstB200BatchResult* r);
+
+/* Device-resident batch (inputs already in HBM; used for kernel-level timing and
+ * for callers that keep a pipeline on the GPU).  All pointers are DEVICE pointers
+ * on the current device; the call is asynchronous on `stream` (a cudaStream_t)
+ * except when an oversized string forces a retry pass (then it synchronises).
+ * Path arrays have capacity `path_capacity` arcs in total; if the batch needs more,
+ * FST_OOM is returned and d_path_offsets[n] holds the required capacity. */
+typedef struct {
+  int32_t* d_status;         /* [n]   */
+  uint64_t* d_path_offsets;  /* [n+1] */
+  uint32_t* d_ilabels;       /* [path_capacity] */
+  uint32_t* d_olabels;       /* [path_capacity] */
+  double* d_weights;         /* [path_capacity] */
+  double* d_final_weights;   /* [n]   */
+  uint32_t* d_n_tuples;      /* [n]   */
+  uint64_t path_capacity;
+} FstB200DeviceOut;
+
+FstError fst_b200_batch_device(FstHandle b, const uint8_t* d_bytes, const uint64_t* d_offsets,
+                               uint32_t n_strings, uint32_t max_len, const FstB200DeviceOut* out,
+                               void* stream);
+
+/* Tuning / introspection (all optional). */
+typedef struct {
+  uint64_t workspace_bytes;   /* device budget for search state; 0 = 60% of free HBM     */
+  uint32_t lanes_per_string;  /* 32, 16, 8, 4; 0 = choose from the transducer's out-degree */
+  uint32_t tuples_hint;       /* expected max tuples per string; 0 = adaptive            */
+  uint32_t exhaustive;        /* 1 = never stop before the queue is empty (reference's
+                                 literal behaviour); 0 = stop once no remaining tuple can
+                                 change the result (identical output, proven in DESIGN.md) */
+} FstB200Config;
+FstError fst_b200_configure(const FstB200Config* cfg);
+/* Counters of the last batched call on this thread: kernels launched, relaxations. */
+void fst_b200_last_counters(uint32_t* launches, uint64_t* relaxations, double* device_ms);
+/* Number of usable CUDA devices (0 => every search call fails loudly). */
+int32_t fst_b200_device_count(void);
+const char* fst_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIBFST_B200_H */

@@ -1,0 +1,571 @@
+// C ABI of libfst_b200.so (declared in include/libfst_b200.h).
+//
+// The drop-in subset mirrors the reference's src/c-api.zig conventions:
+// generation-tagged handles in two separate tables (:109-277), one global mutex
+// for table bookkeeping only (:279-282), left operand snapshotted under the lock
+// (:754), right operand pinned for the duration of a search (:759, :210-248).
+// The search itself runs on the GPU; there is no CPU fallback.
+#include "../../include/libfst_b200.h"
+
+#include <chrono>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "engine.cuh"
+
+using namespace fstb200;
+
+namespace {
+
+// ── generation-tagged handle table (reference src/c-api.zig:109-277) ──
+template <class T>
+class HandleTable {
+ public:
+  uint64_t insert(T* ptr) {
+    uint32_t idx;
+    if (!free_.empty()) {
+      idx = free_.back(); free_.pop_back();
+      gen_[idx]++; if (gen_[idx] == 0) gen_[idx] = 1;
+      slot_[idx] = ptr; pins_[idx] = 0; pending_[idx] = false;
+    } else {
+      idx = (uint32_t)slot_.size();
+      slot_.push_back(ptr); gen_.push_back(1); pins_.push_back(0); pending_.push_back(false);
+    }
+    return ((uint64_t)gen_[idx] << 32) | idx;
+  }
+  T* get(uint64_t h) const { uint32_t i; return validate(h, &i) ? slot_[i] : nullptr; }
+  T* pin(uint64_t h) {
+    uint32_t i;
+    if (!validate(h, &i) || !slot_[i]) return nullptr;
+    pins_[i]++;
+    return slot_[i];
+  }
+  // returns the object to destroy (caller destroys outside any per-object use) or null
+  T* unpin(uint64_t h) {
+    if (h == FST_INVALID_HANDLE) return nullptr;
+    uint32_t i = (uint32_t)(h & 0xFFFFFFFFu);
+    if (i >= slot_.size() || pins_[i] == 0) return nullptr;
+    if (--pins_[i] != 0 || !pending_[i]) return nullptr;
+    T* p = slot_[i]; slot_[i] = nullptr; pending_[i] = false; free_.push_back(i);
+    return p;
+  }
+  // remove: returns the object to destroy now, or null if deferred / invalid
+  T* remove(uint64_t h) {
+    uint32_t i;
+    if (!validate(h, &i) || !slot_[i]) return nullptr;
+    if (pins_[i] > 0) { pending_[i] = true; bump(i); return nullptr; }
+    T* p = slot_[i]; slot_[i] = nullptr; bump(i); free_.push_back(i);
+    return p;
+  }
+  std::vector<T*> drain() {
+    std::vector<T*> all;
+    for (T* p : slot_) if (p) all.push_back(p);
+    slot_.clear(); gen_.clear(); pins_.clear(); pending_.clear(); free_.clear();
+    return all;
+  }
+ private:
+  bool validate(uint64_t h, uint32_t* idx) const {
+    if (h == FST_INVALID_HANDLE) return false;
+    uint32_t g = (uint32_t)(h >> 32), i = (uint32_t)(h & 0xFFFFFFFFu);
+    if (g == 0 || i == 0xFFFFFFFFu || i >= slot_.size()) return false;
+    if (pending_[i] || gen_[i] != g) return false;
+    *idx = i;
+    return true;
+  }
+  void bump(uint32_t i) { gen_[i]++; if (gen_[i] == 0) gen_[i] = 1; }
+  std::vector<T*> slot_; std::vector<uint32_t> gen_, pins_; std::vector<bool> pending_; std::vector<uint32_t> free_;
+};
+
+// A frozen transducer plus its lazily created device images (one per device).
+struct FrozenEntry {
+  std::unique_ptr<HostFrozen> host;
+  std::mutex dev_mu;
+  std::map<int, DeviceFst*> images;
+  ~FrozenEntry() { for (auto& kv : images) free_device_fst(kv.second); }
+  DeviceFst* image_for(int device, cudaError_t* err) {
+    std::lock_guard<std::mutex> lk(dev_mu);
+    auto it = images.find(device);
+    if (it != images.end()) { *err = cudaSuccess; return it->second; }
+    DeviceFst* d = nullptr;
+    *err = upload_fst(*host, device, &d);
+    if (*err != cudaSuccess) return nullptr;
+    images[device] = d;
+    return d;
+  }
+};
+
+std::mutex g_mu;                       // reference api_mutex (src/c-api.zig:282)
+HandleTable<HostMutable> g_mutables;   // src/c-api.zig:276
+HandleTable<FrozenEntry> g_frozen;     // src/c-api.zig:277
+
+thread_local BatchCounters t_last;
+
+bool trace_enabled() {                 // src/c-api.zig:55-64
+  static int v = -1;
+  if (v < 0) v = std::getenv("LIBFST_TRACE_COMPOSE") != nullptr;
+  return v == 1;
+}
+void trace_line(const char* tag, uint64_t a, uint64_t b, size_t in_states, size_t in_arcs, size_t out_states,
+                size_t out_arcs, double us) {   // src/c-api.zig:74-103 (same line format)
+  if (!trace_enabled()) return;
+  std::fprintf(stderr,
+               "[libfst] %s op=fst_compose_frozen a=%llu b=%llu in_states=%zu in_arcs=%zu out_states=%zu out_arcs=%zu elapsed_us=%lld\n",
+               tag, (unsigned long long)a, (unsigned long long)b, in_states, in_arcs, out_states, out_arcs, (long long)us);
+}
+
+uint64_t new_mutable(HostMutable&& m) {
+  auto* p = new (std::nothrow) HostMutable(std::move(m));
+  if (!p) return FST_INVALID_HANDLE;
+  std::lock_guard<std::mutex> lk(g_mu);
+  return g_mutables.insert(p);
+}
+uint64_t new_frozen(std::unique_ptr<HostFrozen> f) {
+  if (!f) return FST_INVALID_HANDLE;
+  auto* e = new (std::nothrow) FrozenEntry();
+  if (!e) return FST_INVALID_HANDLE;
+  e->host = std::move(f);
+  std::lock_guard<std::mutex> lk(g_mu);
+  return g_frozen.insert(e);
+}
+
+bool device_available() {
+  int n = 0;
+  return cudaGetDeviceCount(&n) == cudaSuccess && n > 0;
+}
+
+struct PinGuard {   // unpin on scope exit (src/c-api.zig:777-781)
+  uint64_t h;
+  ~PinGuard() {
+    FrozenEntry* dead;
+    { std::lock_guard<std::mutex> lk(g_mu); dead = g_frozen.unpin(h); }
+    delete dead;
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+// ── mutable lifecycle (src/c-api.zig:436-505) ──
+FstMutableHandle fst_mutable_new(void) { return new_mutable(HostMutable()); }
+
+FstMutableHandle fst_mutable_clone(FstMutableHandle handle) {
+  HostMutable copy;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    HostMutable* m = g_mutables.get(handle);
+    if (!m) return FST_INVALID_HANDLE;
+    copy = *m;
+  }
+  return new_mutable(std::move(copy));
+}
+
+void fst_mutable_free(FstMutableHandle handle) {
+  HostMutable* dead;
+  { std::lock_guard<std::mutex> lk(g_mu); dead = g_mutables.remove(handle); }
+  delete dead;
+}
+
+uint32_t fst_mutable_add_state(FstMutableHandle handle) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  HostMutable* m = g_mutables.get(handle);
+  if (!m) return FST_NO_STATE;
+  return m->add_state();
+}
+
+FstError fst_mutable_set_start(FstMutableHandle handle, uint32_t state) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  HostMutable* m = g_mutables.get(handle);
+  if (!m) return FST_INVALID_ARG;
+  if (state >= m->num_states()) return FST_INVALID_STATE;
+  m->start = state;
+  return FST_OK;
+}
+
+FstError fst_mutable_set_final(FstMutableHandle handle, uint32_t state, double weight) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  HostMutable* m = g_mutables.get(handle);
+  if (!m) return FST_INVALID_ARG;
+  if (state >= m->num_states()) return FST_INVALID_STATE;
+  m->finals[state] = weight;
+  return FST_OK;
+}
+
+FstError fst_mutable_add_arc(FstMutableHandle handle, uint32_t src, uint32_t ilabel, uint32_t olabel, double weight,
+                             uint32_t nextstate) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  HostMutable* m = g_mutables.get(handle);
+  if (!m) return FST_INVALID_ARG;
+  if (src >= m->num_states() || nextstate >= m->num_states()) return FST_INVALID_STATE;
+  m->arcs[src].push_back(HostArc{ilabel, olabel, weight, nextstate});
+  return FST_OK;
+}
+
+// ── mutable queries (src/c-api.zig:1376-1424) ──
+uint32_t fst_mutable_start(FstMutableHandle handle) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  HostMutable* m = g_mutables.get(handle);
+  return m ? m->start : FST_NO_STATE;
+}
+uint32_t fst_mutable_num_states(FstMutableHandle handle) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  HostMutable* m = g_mutables.get(handle);
+  return m ? m->num_states() : 0;
+}
+uint32_t fst_mutable_num_arcs(FstMutableHandle handle, uint32_t state) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  HostMutable* m = g_mutables.get(handle);
+  if (!m || state >= m->num_states()) return 0;
+  return (uint32_t)m->arcs[state].size();
+}
+double fst_mutable_final_weight(FstMutableHandle handle, uint32_t state) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  HostMutable* m = g_mutables.get(handle);
+  if (!m || state >= m->num_states()) return std::numeric_limits<double>::infinity();
+  return m->finals[state];
+}
+uint32_t fst_mutable_get_arcs(FstMutableHandle handle, uint32_t state, FstArc* buf, uint32_t buf_len) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  HostMutable* m = g_mutables.get(handle);
+  if (!m || state >= m->num_states()) return 0;
+  const auto& v = m->arcs[state];
+  uint32_t cnt = std::min<uint32_t>((uint32_t)v.size(), buf_len);
+  if (buf) for (uint32_t i = 0; i < cnt; i++) { buf[i].ilabel = v[i].ilabel; buf[i].olabel = v[i].olabel; buf[i].weight = v[i].weight; buf[i].nextstate = v[i].nextstate; }
+  return cnt;
+}
+
+// ── freeze (src/c-api.zig:507-526) ──
+FstHandle fst_freeze(FstMutableHandle mutable_handle) {
+  HostMutable snap;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    HostMutable* m = g_mutables.get(mutable_handle);
+    if (!m) return FST_INVALID_HANDLE;
+    snap = *m;
+  }
+  return new_frozen(HostFrozen::from_mutable(snap));
+}
+
+// ── frozen lifecycle + queries (src/c-api.zig:530-583) ──
+void fst_free(FstHandle handle) {
+  FrozenEntry* dead;
+  { std::lock_guard<std::mutex> lk(g_mu); dead = g_frozen.remove(handle); }
+  delete dead;
+}
+uint32_t fst_start(FstHandle handle) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  FrozenEntry* f = g_frozen.get(handle);
+  return f ? f->host->start() : FST_NO_STATE;
+}
+uint32_t fst_num_states(FstHandle handle) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  FrozenEntry* f = g_frozen.get(handle);
+  return f ? f->host->num_states() : 0;
+}
+uint32_t fst_num_arcs(FstHandle handle, uint32_t state) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  FrozenEntry* f = g_frozen.get(handle);
+  if (!f || state >= f->host->num_states()) return 0;
+  return f->host->states()[state].num_arcs;
+}
+double fst_final_weight(FstHandle handle, uint32_t state) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  FrozenEntry* f = g_frozen.get(handle);
+  if (!f || state >= f->host->num_states()) return std::numeric_limits<double>::infinity();
+  return f->host->states()[state].final_weight;
+}
+uint32_t fst_get_arcs(FstHandle handle, uint32_t state, FstArc* buf, uint32_t buf_len) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  FrozenEntry* f = g_frozen.get(handle);
+  if (!f || state >= f->host->num_states()) return 0;
+  const ImgState& st = f->host->states()[state];
+  const ImgArc* a = f->host->all_arcs() + st.arc_offset;
+  uint32_t cnt = std::min<uint32_t>(st.num_arcs, buf_len);
+  if (buf) for (uint32_t i = 0; i < cnt; i++) { buf[i].ilabel = a[i].ilabel; buf[i].olabel = a[i].olabel; buf[i].weight = a[i].weight; buf[i].nextstate = a[i].nextstate; }
+  return cnt;
+}
+
+// ── native binary I/O (src/c-api.zig:601-639) ──
+FstHandle fst_load(const char* path) {
+  if (!path) return FST_INVALID_HANDLE;
+  return new_frozen(HostFrozen::load_file(path));
+}
+FstError fst_save(FstHandle handle, const char* path) {
+  if (!path) return FST_INVALID_ARG;
+  FrozenEntry* f;
+  { std::lock_guard<std::mutex> lk(g_mu); f = g_frozen.pin(handle); }
+  if (!f) return FST_INVALID_ARG;
+  PinGuard pg{handle};
+  return f->host->save_file(path) ? FST_OK : FST_IO_ERROR;
+}
+
+// ── string helpers (src/c-api.zig:1334-1372) ──
+FstMutableHandle fst_compile_string(const uint8_t* input, uint32_t len) {
+  if (!input) return FST_INVALID_HANDLE;
+  return new_mutable(HostMutable::from_bytes_string(input, len));
+}
+static int32_t print_tape(FstMutableHandle handle, bool output, uint8_t* buf, uint32_t buf_len) {
+  std::string s;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    HostMutable* m = g_mutables.get(handle);
+    if (!m) return -1;
+    if (!m->print_tape(output, &s)) return -1;
+  }
+  if (s.size() > buf_len) return -1;
+  if (buf && !s.empty()) std::memcpy(buf, s.data(), s.size());
+  return (int32_t)s.size();
+}
+int32_t fst_print_string(FstMutableHandle handle, uint8_t* buf, uint32_t buf_len) { return print_tape(handle, false, buf, buf_len); }
+int32_t fst_print_output_string(FstMutableHandle handle, uint8_t* buf, uint32_t buf_len) { return print_tape(handle, true, buf, buf_len); }
+
+// ── THE HOT PATH, single problem (src/c-api.zig:744-811) ──
+FstMutableHandle fst_compose_frozen_shortest_path(FstMutableHandle a_handle, FstHandle b_handle, uint32_t n) {
+  const bool trace = trace_enabled();
+  auto t0 = std::chrono::steady_clock::now();
+  auto us = [&]() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(); };
+  HostMutable a;
+  FrozenEntry* fb;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    HostMutable* pa = g_mutables.get(a_handle);
+    if (!pa) { trace_line("sp_invalid_a", a_handle, b_handle, 0, 0, 0, 0, us()); return FST_INVALID_HANDLE; }
+    a = *pa;   // snapshot under the lock (:754)
+    fb = g_frozen.pin(b_handle);
+    if (!fb) { trace_line("sp_invalid_b", a_handle, b_handle, a.num_states(), a.total_arcs(), 0, 0, us()); return FST_INVALID_HANDLE; }
+  }
+  PinGuard pg{b_handle};
+  const size_t in_states = a.num_states(), in_arcs = a.total_arcs();
+  auto fail = [&]() { trace_line("sp_compose_error", a_handle, b_handle, in_states, in_arcs, 0, 0, us()); return FST_INVALID_HANDLE; };
+
+  HostMutable result;
+  // compose-shortest-path.zig:30-33
+  if (a.start == kNoState || fb->host->start() == kNoState || n == 0) {
+    // empty FST
+  } else if (n != 1) {
+    return fail();
+  } else {
+    // documented deviations: NaN weights are rejected (reference: UB in math.order);
+    // left-operand state ids must fit 30 bits (tuple key packing).
+    bool lhs_neg = false, lhs_nan = false;
+    for (uint32_t s = 0; s < a.num_states(); s++) {
+      if (std::isnan(a.finals[s])) lhs_nan = true;
+      if (a.finals[s] < 0) lhs_neg = true;
+      for (const HostArc& x : a.arcs[s]) { if (std::isnan(x.weight)) lhs_nan = true; if (x.weight < 0) lhs_neg = true; }
+    }
+    if (lhs_nan || fb->host->has_nan || a.num_states() >= (1u << 30)) return fail();
+    if (!device_available()) {
+      std::fprintf(stderr, "[libfst_b200] no CUDA device: fst_compose_frozen_shortest_path has no CPU fallback\n");
+      return fail();
+    }
+    cudaError_t err;
+    Engine* en = Engine::for_current_device(&err);
+    if (!en) return fail();
+    DeviceFst* img = fb->image_for(en->device, &err);
+    if (!img) return fail();
+    int32_t status = kStNoPath; double fw = 0;
+    std::vector<uint32_t> il, ol; std::vector<double> w;
+    {
+      std::lock_guard<std::mutex> lk(en->mu);
+      BatchCounters bc;
+      err = en->run_general(img, a, lhs_neg, &status, &il, &ol, &w, &fw, &bc);
+      t_last = bc;
+    }
+    if (err != cudaSuccess) return fail();
+    if (status == kStPath) result = HostMutable::chain(il.data(), ol.data(), w.data(), il.size(), fw);
+    else if (status == kStNoPath) { /* empty */ }
+    else return fail();   // cycle hazard (reference: OOM) or too large
+  }
+  trace_line("sp_ok", a_handle, b_handle, in_states, in_arcs, result.num_states(), result.total_arcs(), us());
+  uint64_t h = new_mutable(std::move(result));
+  if (h == FST_INVALID_HANDLE) trace_line("sp_new_handle_oom", a_handle, b_handle, in_states, in_arcs, 0, 0, us());
+  return h;
+}
+
+// ── teardown (src/c-api.zig:295-329) ──
+void fst_teardown(void) {
+  std::vector<HostMutable*> ms; std::vector<FrozenEntry*> fs;
+  { std::lock_guard<std::mutex> lk(g_mu); ms = g_mutables.drain(); fs = g_frozen.drain(); }
+  for (auto* p : ms) delete p;
+  for (auto* p : fs) delete p;
+  if (device_available()) {
+    cudaError_t err;
+    Engine* en = Engine::for_current_device(&err);
+    if (en) { std::lock_guard<std::mutex> lk(en->mu); en->release_all(); }
+  }
+}
+
+// ── batched entry points ──
+struct BatchResultImpl {
+  FstB200BatchResult pub;
+  void* pinned = nullptr;   // one pinned allocation backing all arrays
+};
+
+static int32_t map_status(int32_t s) {
+  switch (s) { case kStPath: return FST_B200_PATH; case kStNoPath: return FST_B200_NO_PATH; case kStCycle: return FST_B200_CYCLE; default: return FST_B200_TOO_LARGE; }
+}
+
+FstError fst_compose_frozen_shortest_path_batch(FstHandle b, const uint8_t* bytes, const uint64_t* offsets,
+                                                uint32_t n_strings, FstB200BatchResult** out) {
+  if (!out) return FST_INVALID_ARG;
+  *out = nullptr;
+  if (!offsets || (!bytes && n_strings && offsets[n_strings] > 0)) return FST_INVALID_ARG;
+  for (uint32_t i = 0; i < n_strings; i++) if (offsets[i + 1] < offsets[i]) return FST_INVALID_ARG;
+  FrozenEntry* fb;
+  { std::lock_guard<std::mutex> lk(g_mu); fb = g_frozen.pin(b); }
+  if (!fb) return FST_INVALID_ARG;
+  PinGuard pg{b};
+  if (fb->host->has_nan) return FST_INVALID_ARG;
+  if (!device_available()) {
+    std::fprintf(stderr, "[libfst_b200] no CUDA device: the batched search has no CPU fallback\n");
+    return FST_INVALID_STATE;
+  }
+  cudaError_t err;
+  Engine* en = Engine::for_current_device(&err);
+  if (!en) return FST_INVALID_STATE;
+  DeviceFst* img = fb->image_for(en->device, &err);
+  if (!img) return err == cudaErrorMemoryAllocation ? FST_OOM : FST_INVALID_STATE;
+
+  const uint64_t nbytes = n_strings ? offsets[n_strings] - offsets[0] : 0;
+  uint64_t max_len = 0;
+  for (uint32_t i = 0; i < n_strings; i++) max_len = std::max<uint64_t>(max_len, offsets[i + 1] - offsets[i]);
+  if (max_len >= (1u << 30)) return FST_INVALID_ARG;
+
+  std::lock_guard<std::mutex> lk(en->mu);
+  cudaStream_t stream = 0;
+  const uint32_t n = n_strings;
+  // device buffers for this call
+  uint8_t* d_bytes = nullptr; uint64_t* d_offsets = nullptr; int32_t* d_status = nullptr; uint64_t* d_poff = nullptr;
+  uint32_t *d_il = nullptr, *d_ol = nullptr, *d_nt = nullptr; double *d_w = nullptr, *d_fin = nullptr;
+  uint64_t* d_ooff = nullptr; uint8_t* d_obytes = nullptr;
+  std::vector<uint64_t> rel(n + 1);
+  for (uint32_t i = 0; i <= n; i++) rel[i] = offsets[i] - offsets[0];
+  uint64_t path_cap = 2 * nbytes + 16ull * n + 1024;
+  auto free_dev = [&]() {
+    cudaFree(d_bytes); cudaFree(d_offsets); cudaFree(d_status); cudaFree(d_poff); cudaFree(d_il); cudaFree(d_ol); cudaFree(d_nt);
+    cudaFree(d_w); cudaFree(d_fin); cudaFree(d_ooff); cudaFree(d_obytes);
+    d_bytes = nullptr; d_offsets = nullptr; d_status = nullptr; d_poff = nullptr; d_il = d_ol = d_nt = nullptr; d_w = d_fin = nullptr; d_ooff = nullptr; d_obytes = nullptr;
+  };
+  BatchCounters bc;
+  for (int attempt = 0;; attempt++) {
+    bool ok = cudaMalloc(&d_bytes, nbytes + 16) == cudaSuccess && cudaMalloc(&d_offsets, (size_t)(n + 1) * 8) == cudaSuccess &&
+              cudaMalloc(&d_status, (size_t)n * 4 + 16) == cudaSuccess && cudaMalloc(&d_poff, (size_t)(n + 1) * 8) == cudaSuccess &&
+              cudaMalloc(&d_il, path_cap * 4) == cudaSuccess && cudaMalloc(&d_ol, path_cap * 4) == cudaSuccess &&
+              cudaMalloc(&d_w, path_cap * 8) == cudaSuccess && cudaMalloc(&d_fin, (size_t)n * 8 + 16) == cudaSuccess &&
+              cudaMalloc(&d_nt, (size_t)n * 4 + 16) == cudaSuccess && cudaMalloc(&d_ooff, (size_t)(n + 1) * 8) == cudaSuccess &&
+              cudaMalloc(&d_obytes, path_cap + 16) == cudaSuccess;
+    if (!ok) { cudaGetLastError(); free_dev(); return FST_OOM; }
+    if (nbytes) cudaMemcpyAsync(d_bytes, bytes + offsets[0], nbytes, cudaMemcpyHostToDevice, stream);
+    cudaMemcpyAsync(d_offsets, rel.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, stream);
+    err = en->run_batch(img, d_bytes, d_offsets, n, d_status, d_poff, d_il, d_ol, d_w, d_fin, d_nt, path_cap, d_ooff, d_obytes, path_cap, stream, &bc);
+    if (err != cudaSuccess) { free_dev(); return err == cudaErrorMemoryAllocation ? FST_OOM : FST_INVALID_STATE; }
+    if (bc.path_required > path_cap && attempt < 4) { path_cap = bc.path_required * 2; free_dev(); continue; }
+    break;
+  }
+  t_last = bc;
+  // assemble the pinned host result
+  const uint64_t total = bc.path_total;
+  uint64_t out_total = 0;
+  if (n) cudaMemcpy(&out_total, d_ooff + n, 8, cudaMemcpyDeviceToHost);
+  auto al = [](size_t x) { return (x + 63) & ~(size_t)63; };
+  size_t o_status = 0, o_poff = o_status + al((size_t)n * 4), o_il = o_poff + al((size_t)(n + 1) * 8), o_ol = o_il + al(total * 4),
+         o_w = o_ol + al(total * 4), o_fin = o_w + al(total * 8), o_nt = o_fin + al((size_t)n * 8), o_ooff = o_nt + al((size_t)n * 4),
+         o_ob = o_ooff + al((size_t)(n + 1) * 8), bytes_total = o_ob + al(out_total) + 64;
+  auto* r = new (std::nothrow) BatchResultImpl();
+  if (!r || cudaMallocHost(&r->pinned, bytes_total) != cudaSuccess) { delete r; free_dev(); return FST_OOM; }
+  uint8_t* hb = static_cast<uint8_t*>(r->pinned);
+  if (n) {
+    cudaMemcpyAsync(hb + o_status, d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, stream);
+    cudaMemcpyAsync(hb + o_fin, d_fin, (size_t)n * 8, cudaMemcpyDeviceToHost, stream);
+    cudaMemcpyAsync(hb + o_nt, d_nt, (size_t)n * 4, cudaMemcpyDeviceToHost, stream);
+  }
+  cudaMemcpyAsync(hb + o_poff, d_poff, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, stream);
+  cudaMemcpyAsync(hb + o_ooff, d_ooff, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, stream);
+  if (total) {
+    cudaMemcpyAsync(hb + o_il, d_il, total * 4, cudaMemcpyDeviceToHost, stream);
+    cudaMemcpyAsync(hb + o_ol, d_ol, total * 4, cudaMemcpyDeviceToHost, stream);
+    cudaMemcpyAsync(hb + o_w, d_w, total * 8, cudaMemcpyDeviceToHost, stream);
+  }
+  if (out_total) cudaMemcpyAsync(hb + o_ob, d_obytes, out_total, cudaMemcpyDeviceToHost, stream);
+  err = cudaStreamSynchronize(stream);
+  free_dev();
+  if (err != cudaSuccess) { cudaFreeHost(r->pinned); delete r; return FST_INVALID_STATE; }
+  int32_t* hs = reinterpret_cast<int32_t*>(hb + o_status);
+  for (uint32_t i = 0; i < n; i++) hs[i] = map_status(hs[i]);
+  r->pub.n_strings = n;
+  r->pub.status = hs;
+  r->pub.path_offsets = reinterpret_cast<uint64_t*>(hb + o_poff);
+  r->pub.ilabels = reinterpret_cast<uint32_t*>(hb + o_il);
+  r->pub.olabels = reinterpret_cast<uint32_t*>(hb + o_ol);
+  r->pub.weights = reinterpret_cast<double*>(hb + o_w);
+  r->pub.final_weights = reinterpret_cast<double*>(hb + o_fin);
+  r->pub.n_tuples = reinterpret_cast<uint32_t*>(hb + o_nt);
+  r->pub.out_offsets = reinterpret_cast<uint64_t*>(hb + o_ooff);
+  r->pub.out_bytes = hb + o_ob;
+  r->pub.device_ms = bc.device_ms;
+  r->pub.total_tuples = bc.tuples;
+  r->pub.total_relax = bc.relax;
+  r->pub.launches = bc.launches;
+  r->pub.passes = bc.passes;
+  *out = &r->pub;
+  return FST_OK;
+}
+
+void fst_b200_batch_free(FstB200BatchResult* r) {
+  if (!r) return;
+  auto* impl = reinterpret_cast<BatchResultImpl*>(r);   // pub is the first member
+  cudaFreeHost(impl->pinned);
+  delete impl;
+}
+
+FstError fst_b200_batch_device(FstHandle b, const uint8_t* d_bytes, const uint64_t* d_offsets, uint32_t n_strings,
+                               uint32_t max_len, const FstB200DeviceOut* o, void* stream) {
+  if (!o || !d_offsets || !o->d_status || !o->d_path_offsets || !o->d_final_weights || !o->d_n_tuples) return FST_INVALID_ARG;
+  if (max_len >= (1u << 30)) return FST_INVALID_ARG;
+  FrozenEntry* fb;
+  { std::lock_guard<std::mutex> lk(g_mu); fb = g_frozen.pin(b); }
+  if (!fb) return FST_INVALID_ARG;
+  PinGuard pg{b};
+  if (fb->host->has_nan) return FST_INVALID_ARG;
+  if (!device_available()) return FST_INVALID_STATE;
+  cudaError_t err;
+  Engine* en = Engine::for_current_device(&err);
+  if (!en) return FST_INVALID_STATE;
+  DeviceFst* img = fb->image_for(en->device, &err);
+  if (!img) return err == cudaErrorMemoryAllocation ? FST_OOM : FST_INVALID_STATE;
+  std::lock_guard<std::mutex> lk(en->mu);
+  BatchCounters bc;
+  err = en->run_batch(img, d_bytes, d_offsets, n_strings, o->d_status, o->d_path_offsets, o->d_ilabels, o->d_olabels, o->d_weights,
+                      o->d_final_weights, o->d_n_tuples, o->path_capacity, nullptr, nullptr, 0, static_cast<cudaStream_t>(stream), &bc);
+  t_last = bc;
+  if (err != cudaSuccess) return err == cudaErrorMemoryAllocation ? FST_OOM : FST_INVALID_STATE;
+  if (bc.path_required > o->path_capacity || bc.path_total > o->path_capacity) return FST_OOM;
+  return FST_OK;
+}
+
+FstError fst_b200_configure(const FstB200Config* cfg) {
+  if (!cfg) return FST_INVALID_ARG;
+  uint32_t g = cfg->lanes_per_string;
+  if (!(g == 0 || g == 4 || g == 8 || g == 16 || g == 32)) return FST_INVALID_ARG;
+  Config& c = global_config();
+  c.workspace_bytes = cfg->workspace_bytes; c.lanes_per_string = g; c.tuples_hint = cfg->tuples_hint; c.exhaustive = cfg->exhaustive;
+  return FST_OK;
+}
+
+void fst_b200_last_counters(uint32_t* launches, uint64_t* relaxations, double* device_ms) {
+  if (launches) *launches = t_last.launches;
+  if (relaxations) *relaxations = t_last.relax;
+  if (device_ms) *device_ms = t_last.device_ms;
+}
+
+int32_t fst_b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+const char* fst_b200_version(void) { return "libfst_b200 0.1 (sm_100a)"; }
+
+}  // extern "C"

@@ -1,0 +1,107 @@
+// Device-side data layout shared by the upload code, the kernels and the engine.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace fstb200 {
+
+constexpr uint32_t kNone = 0xFFFFFFFFu;
+
+// Frozen transducer in HBM (struct-of-arrays CSR, frozen arc order unchanged —
+// reference src/fst.zig:16-40 and SURVEY App. D):
+//   state_rec[s] = {arc_begin, eps_end, arc_end, 0}   absolute arc indices; the
+//                  arcs [arc_begin, eps_end) are the state's ilabel==0 prefix
+//                  (valid because frozen arcs are ilabel-sorted, src/arc.zig:46-54)
+//   final_w[s]   = f64 final weight (+inf = not final)
+//   ilabel[a]    = u32 search key array (binary-searched, src/fst.zig:112-136)
+//   payload[a]   = {olabel, nextstate, weight(f64 as 2xu32)} one 16-byte vector load
+struct DevFstView {
+  uint32_t num_states, num_arcs, start, max_degree;
+  const uint4* state_rec;
+  const double* final_w;
+  const uint32_t* ilabel;
+  const uint4* payload;
+};
+
+// General (non-linear) left operand as CSR in STORED arc order
+// (reference src/mutable-fst.zig:183 `arcs`, no sorting).
+struct DevLhsCsr {
+  uint32_t num_states, num_arcs, start, pad;
+  const uint32_t* arc_off;  // [S+1]
+  const double* final_w;    // [S]
+  const uint32_t* ilabel;   // [A]
+  const uint32_t* olabel;   // [A]
+  const double* weight;     // [A]
+  const uint32_t* next;     // [A]
+};
+
+// One search-state record: a slot of the per-string open-addressing table.
+// 32 bytes = one DRAM sector: a relaxation touches exactly one sector.
+struct __align__(32) TupleSlot {
+  unsigned long long key;  // (s1 << 34) | (s2 << 2) | filter ; all-ones = empty
+  double dist;             // tentative / final distance (tropical)
+  uint32_t id_flags;       // discovery-order id (bits 0..30) | settled (bit 31)
+  uint32_t prev_id;        // back-pointer: predecessor id, kNone = no back-pointer
+  uint32_t rhs_arc;        // back-pointer: transducer arc index or kNone
+  uint32_t lhs_arc;        // back-pointer: left-operand arc index or kNone
+};
+static_assert(sizeof(TupleSlot) == 32, "TupleSlot must be one 32-byte sector");
+
+constexpr unsigned long long kEmptyKey = ~0ull;
+constexpr uint32_t kSettledBit = 0x80000000u;
+
+// Per-string status written by the search kernel (internal; the C ABI maps
+// kRetry to a retry pass and finally to FST_B200_TOO_LARGE).
+enum : int32_t { kStPath = 0, kStNoPath = 1, kStCycle = 2, kStTooLarge = 3, kStRetry = 100 };
+
+// Reversed path arc as written to the path pool by the search kernel.
+struct __align__(16) PoolArc { uint32_t ilabel, olabel; double weight; };
+
+struct SearchParams {
+  DevFstView fst;
+  // batch of byte strings (linear left operands, label = byte + 1)
+  const uint8_t* bytes;
+  const uint64_t* offsets;
+  const uint32_t* order;   // optional: work item i -> string index (retry passes); null = identity
+  uint32_t n_items;
+  // or: one general left operand (n_items == 1, bytes == nullptr)
+  DevLhsCsr lhs;
+  // per-group arenas
+  uint8_t* arena;
+  uint64_t arena_stride;
+  uint32_t hash_cap;       // power of two
+  uint32_t tuple_cap;
+  uint32_t heap_cap;
+  uint32_t exhaustive;
+  // work queue + counters
+  uint32_t* queue_head;
+  unsigned long long* pool_cursor;
+  unsigned long long* relax_counter;
+  unsigned long long* tuple_counter;
+  // outputs (indexed by string index)
+  int32_t* status;
+  uint32_t* path_len;
+  uint64_t* pool_off;
+  double* final_w;
+  uint32_t* n_tuples;
+  PoolArc* pool;
+  uint64_t pool_cap;
+};
+
+struct EmitParams {
+  const int32_t* status;
+  const uint32_t* path_len;
+  const uint64_t* pool_off;
+  const uint64_t* path_offsets;  // exclusive scan of path_len, [n+1]
+  const PoolArc* pool;
+  uint32_t n_strings;
+  uint32_t* ilabels;
+  uint32_t* olabels;
+  double* weights;
+  uint64_t path_capacity;
+  // optional fused output-tape string (label-1, epsilons dropped)
+  const uint64_t* out_offsets;   // exclusive scan of out_len
+  uint8_t* out_bytes;
+};
+
+}  // namespace fstb200

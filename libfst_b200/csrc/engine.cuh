@@ -1,0 +1,493 @@
+// Host-side engine: device image of a frozen transducer, per-device workspace,
+// pass scheduling (adaptive arena sizing + retry of oversized strings), result
+// assembly.  One Engine per CUDA device per process; calls are serialised per
+// device by a mutex (the reference's frozen queries are re-entrant; here the GPU
+// is the shared resource).
+#pragma once
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "csp_kernels.cuh"
+#include "host_fst.hpp"
+
+namespace fstb200 {
+
+#define FSTB_CUDA(expr)                                                                         \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess) {                                                                    \
+      std::fprintf(stderr, "[libfst_b200] CUDA error %s at %s:%d: %s\n", cudaGetErrorName(_e), \
+                   __FILE__, __LINE__, cudaGetErrorString(_e));                                 \
+      return _e;                                                                                \
+    }                                                                                           \
+  } while (0)
+
+struct Config {
+  uint64_t workspace_bytes = 0;
+  uint32_t lanes_per_string = 0;
+  uint32_t tuples_hint = 0;
+  uint32_t exhaustive = 0;
+};
+inline Config& global_config() { static Config c; return c; }
+
+// ── device image of a frozen transducer ──
+struct DeviceFst {
+  int device = -1;
+  DevFstView view{};
+  void* block = nullptr;   // one allocation holding all arrays
+  size_t bytes = 0;
+  bool serial = false;     // negative weights: literal sequential relax
+  uint32_t hint_tuples = 0;  // largest per-string tuple count seen so far (arena sizing)
+};
+
+inline cudaError_t upload_fst(const HostFrozen& f, int device, DeviceFst** out) {
+  *out = nullptr;
+  const uint32_t S = f.num_states(), A = f.num_arcs();
+  const ImgState* st = f.states(); const ImgArc* ar = f.all_arcs();
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  size_t o_rec = 0, o_fin = o_rec + al((size_t)S * 16), o_il = o_fin + al((size_t)S * 8), o_pl = o_il + al((size_t)A * 4);
+  size_t total = o_pl + al((size_t)A * 16) + 256;
+  std::vector<uint8_t> h(total, 0);
+  uint4* rec = reinterpret_cast<uint4*>(h.data() + o_rec);
+  double* fin = reinterpret_cast<double*>(h.data() + o_fin);
+  uint32_t* il = reinterpret_cast<uint32_t*>(h.data() + o_il);
+  uint4* pl = reinterpret_cast<uint4*>(h.data() + o_pl);
+  uint32_t maxdeg = 0;
+  for (uint32_t s = 0; s < S; s++) {
+    uint32_t b = st[s].arc_offset, e = b + st[s].num_arcs, ee = b;
+    while (ee < e && ar[ee].ilabel == 0) ee++;   // epsilon prefix (arcs are ilabel-sorted)
+    rec[s] = make_uint4(b, ee, e, 0);
+    fin[s] = st[s].final_weight;
+    maxdeg = std::max(maxdeg, st[s].num_arcs);
+  }
+  for (uint32_t a = 0; a < A; a++) {
+    il[a] = ar[a].ilabel;
+    unsigned long long wb; std::memcpy(&wb, &ar[a].weight, 8);
+    pl[a] = make_uint4(ar[a].olabel, ar[a].nextstate, (uint32_t)(wb & 0xFFFFFFFFu), (uint32_t)(wb >> 32));
+  }
+  auto d = new DeviceFst();
+  d->device = device; d->bytes = total; d->serial = f.has_negative;
+  cudaError_t e = cudaMalloc(&d->block, total);
+  if (e != cudaSuccess) { delete d; return e; }
+  e = cudaMemcpy(d->block, h.data(), total, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(d->block); delete d; return e; }
+  uint8_t* base = static_cast<uint8_t*>(d->block);
+  d->view.num_states = S; d->view.num_arcs = A; d->view.start = f.start(); d->view.max_degree = maxdeg;
+  d->view.state_rec = reinterpret_cast<const uint4*>(base + o_rec);
+  d->view.final_w = reinterpret_cast<const double*>(base + o_fin);
+  d->view.ilabel = reinterpret_cast<const uint32_t*>(base + o_il);
+  d->view.payload = reinterpret_cast<const uint4*>(base + o_pl);
+  *out = d;
+  return cudaSuccess;
+}
+inline void free_device_fst(DeviceFst* d) {
+  if (!d) return;
+  int cur = 0; cudaGetDevice(&cur);
+  if (cur != d->device) cudaSetDevice(d->device);
+  cudaFree(d->block);
+  if (cur != d->device) cudaSetDevice(cur);
+  delete d;
+}
+
+// small helper kernels (plumbing)
+__global__ void collect_retry_kernel(const int32_t* status, uint32_t n, uint32_t* order, uint32_t* count) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && status[i] == kStRetry) order[atomicAdd(count, 1u)] = i;
+}
+__global__ void mark_too_large_kernel(int32_t* status, uint32_t* path_len, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && status[i] == kStRetry) { status[i] = kStTooLarge; path_len[i] = 0; }
+}
+__global__ void fill_retry_kernel(int32_t* status, uint32_t* path_len, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { status[i] = kStRetry; path_len[i] = 0; }
+}
+__global__ void widen_kernel(const uint32_t* in, uint64_t* out, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i];
+}
+__global__ void max_u32_kernel(const uint32_t* in, uint32_t n, uint32_t* out) {
+  uint32_t m = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = max(m, in[i]);
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+struct BatchCounters {
+  uint32_t launches = 0, passes = 0;
+  unsigned long long relax = 0, tuples = 0;
+  double device_ms = 0;
+  uint64_t path_total = 0, path_required = 0;
+  uint32_t max_tuples = 0;
+};
+
+class Engine {
+ public:
+  int device = 0;
+  int sm_count = 0;
+  std::mutex mu;
+
+  static Engine* for_current_device(cudaError_t* err) {
+    static std::mutex gm;
+    static std::map<int, Engine*> engines;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) { *err = e; return nullptr; }
+    std::lock_guard<std::mutex> lk(gm);
+    auto it = engines.find(dev);
+    if (it != engines.end()) { *err = cudaSuccess; return it->second; }
+    auto en = new Engine();
+    en->device = dev;
+    e = cudaDeviceGetAttribute(&en->sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) { delete en; *err = e; return nullptr; }
+    e = cudaMalloc(&en->d_small_, 256);
+    if (e != cudaSuccess) { delete en; *err = e; return nullptr; }
+    e = cudaMallocHost(&en->h_small_, 256);
+    if (e != cudaSuccess) { delete en; *err = e; return nullptr; }
+    cudaEventCreate(&en->ev0_); cudaEventCreate(&en->ev1_);
+    engines[dev] = en;
+    *err = cudaSuccess;
+    return en;
+  }
+
+  // Device-resident batch.  All d_* pointers are device memory on this device.
+  // Synchronises `stream` before returning (the retry decision needs a read-back).
+  cudaError_t run_batch(DeviceFst* fst, const uint8_t* d_bytes, const uint64_t* d_offsets, uint32_t n,
+                        int32_t* d_status, uint64_t* d_path_offsets, uint32_t* d_il, uint32_t* d_ol, double* d_w,
+                        double* d_final, uint32_t* d_ntuples, uint64_t path_capacity,
+                        uint64_t* d_out_offsets, uint8_t* d_out_bytes, uint64_t out_capacity,
+                        cudaStream_t stream, BatchCounters* bc) {
+    *bc = BatchCounters();
+    if (n == 0) {
+      FSTB_CUDA(cudaMemsetAsync(d_path_offsets, 0, 8, stream));
+      if (d_out_offsets) FSTB_CUDA(cudaMemsetAsync(d_out_offsets, 0, 8, stream));
+      return cudaStreamSynchronize(stream);
+    }
+    const Config cfg = global_config();
+    FSTB_CUDA(ensure_scratch(n, path_capacity));
+    // counters: [0] queue_head(u32) [1] retry_count(u32) [2..3] pool_cursor(u64) [4..5] relax [6..7] tuples [8] max_tuples
+    uint32_t* d_cnt = static_cast<uint32_t*>(d_small_);
+    FSTB_CUDA(cudaMemsetAsync(d_cnt, 0, 64, stream));
+    FSTB_CUDA(cudaEventRecord(ev0_, stream));
+    fill_retry_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_status, d_path_len_, n);
+    bc->launches++;
+
+    uint32_t G = choose_lanes(cfg, fst);
+    uint32_t tuple_cap = cfg.tuples_hint ? cfg.tuples_hint : (fst->hint_tuples ? fst->hint_tuples + fst->hint_tuples / 4 + 64 : 4096);
+    uint32_t n_items = n;
+    const uint32_t* d_order = nullptr;
+    for (uint32_t pass = 0;; pass++) {
+      bc->passes++;
+      uint32_t hash_cap = 1024;
+      while ((uint64_t)hash_cap * 6 / 10 < tuple_cap && hash_cap < (1u << 31)) hash_cap <<= 1;
+      tuple_cap = (uint32_t)((uint64_t)hash_cap * 6 / 10);
+      uint32_t heap_cap = tuple_cap * 3;
+      uint64_t stride = arena_bytes(hash_cap, tuple_cap, heap_cap);
+      uint32_t max_groups = max_resident_groups(G, fst->serial);
+      uint32_t want = std::min<uint32_t>(n_items, max_groups);
+      uint64_t ws = workspace_budget(cfg);
+      uint32_t fit = (uint32_t)std::min<uint64_t>(ws / stride, 0xFFFFFFFFull);
+      if (fit == 0) {
+        // even one arena does not fit: these strings are too large for the budget
+        mark_too_large_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_status, d_path_len_, n);
+        bc->launches++;
+        break;
+      }
+      // full 128-thread blocks when the budget allows, else one partial block
+      uint32_t gpb = 128 / G, threads = 128, blocks;
+      if (fit >= gpb) {
+        blocks = std::min((want + gpb - 1) / gpb, fit / gpb);
+      } else {
+        blocks = 1; gpb = std::min(want, fit); threads = gpb * G;
+      }
+      FSTB_CUDA(ensure_workspace((uint64_t)blocks * gpb * stride, hash_cap, tuple_cap, stride, blocks * gpb, stream));
+
+      SearchParams p{};
+      p.fst = fst->view;
+      p.bytes = d_bytes; p.offsets = d_offsets; p.order = d_order; p.n_items = n_items;
+      p.arena = static_cast<uint8_t*>(d_workspace_); p.arena_stride = stride;
+      p.hash_cap = hash_cap; p.tuple_cap = tuple_cap; p.heap_cap = heap_cap; p.exhaustive = cfg.exhaustive;
+      p.queue_head = d_cnt + 0;
+      p.pool_cursor = reinterpret_cast<unsigned long long*>(d_cnt + 2);
+      p.relax_counter = reinterpret_cast<unsigned long long*>(d_cnt + 4);
+      p.tuple_counter = reinterpret_cast<unsigned long long*>(d_cnt + 6);
+      p.status = d_status; p.path_len = d_path_len_; p.pool_off = d_pool_off_; p.final_w = d_final; p.n_tuples = d_ntuples;
+      p.pool = d_pool_; p.pool_cap = pool_cap_;
+      launch_search(G, fst->serial, blocks, threads, p, stream);
+      bc->launches++;
+      FSTB_CUDA(cudaGetLastError());
+      // any string that overflowed its arena (or the pool)?
+      FSTB_CUDA(cudaMemsetAsync(d_cnt + 1, 0, 4, stream));
+      collect_retry_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_status, n, d_order_buf_[pass & 1], d_cnt + 1);
+      bc->launches++;
+      FSTB_CUDA(cudaMemcpyAsync(h_small_, d_cnt, 64, cudaMemcpyDeviceToHost, stream));
+      FSTB_CUDA(cudaStreamSynchronize(stream));
+      const uint32_t* hc = static_cast<const uint32_t*>(h_small_);
+      uint32_t retry = hc[1];
+      unsigned long long pool_used; std::memcpy(&pool_used, hc + 2, 8);
+      if (retry == 0) break;
+      if (pool_used > pool_cap_) {
+        // path pool too small: report the requirement; caller grows and re-runs
+        bc->path_required = pool_used;
+        mark_too_large_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_status, d_path_len_, n);
+        bc->launches++;
+        break;
+      }
+      // next pass: only the overflowed strings, 8x larger arenas
+      n_items = retry;
+      d_order = d_order_buf_[pass & 1];
+      if (tuple_cap > (1u << 31) / 8) { mark_too_large_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_status, d_path_len_, n); bc->launches++; break; }
+      tuple_cap *= 8;
+      FSTB_CUDA(cudaMemsetAsync(d_cnt + 0, 0, 4, stream));   // queue head
+    }
+
+    // ordered output: offsets = exclusive scan of path lengths, then un-reverse
+    widen_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_path_len_, d_len64_, n);
+    FSTB_CUDA(cudaMemsetAsync(d_len64_ + n, 0, 8, stream));
+    size_t tmp = scan_tmp_bytes_;
+    FSTB_CUDA(cub::DeviceScan::ExclusiveSum(d_scan_tmp_, tmp, d_len64_, d_path_offsets, (int)(n + 1), stream));
+    bc->launches += 2;
+    EmitParams e{};
+    e.status = d_status; e.path_len = d_path_len_; e.pool_off = d_pool_off_; e.path_offsets = d_path_offsets; e.pool = d_pool_;
+    e.n_strings = n; e.ilabels = d_il; e.olabels = d_ol; e.weights = d_w; e.path_capacity = path_capacity;
+    e.out_offsets = nullptr; e.out_bytes = nullptr;
+    if (d_out_offsets && d_out_bytes) {
+      csp_count_out_kernel<<<std::min<uint32_t>((n + 7) / 8, 148 * 16), 256, 0, stream>>>(d_status, d_path_len_, d_pool_off_, d_pool_, n, d_out_len_);
+      widen_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_out_len_, d_len64_, n);
+      FSTB_CUDA(cub::DeviceScan::ExclusiveSum(d_scan_tmp_, tmp, d_len64_, d_out_offsets, (int)(n + 1), stream));
+      bc->launches += 3;
+      e.out_offsets = d_out_offsets; e.out_bytes = d_out_bytes;
+      (void)out_capacity;   // out bytes <= path arcs <= path_capacity; caller sizes it so
+    }
+    csp_emit_kernel<<<std::min<uint32_t>((n + 7) / 8, 148 * 16), 256, 0, stream>>>(e);
+    bc->launches++;
+    max_u32_kernel<<<std::min<uint32_t>((n + 255) / 256, 592), 256, 0, stream>>>(d_ntuples, n, d_cnt + 8);
+    bc->launches++;
+    FSTB_CUDA(cudaEventRecord(ev1_, stream));
+    FSTB_CUDA(cudaMemcpyAsync(h_small_, d_cnt, 64, cudaMemcpyDeviceToHost, stream));
+    FSTB_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(h_small_) + 64, d_path_offsets + n, 8, cudaMemcpyDeviceToHost, stream));
+    FSTB_CUDA(cudaStreamSynchronize(stream));
+    FSTB_CUDA(cudaGetLastError());
+    const uint32_t* hc = static_cast<const uint32_t*>(h_small_);
+    std::memcpy(&bc->relax, hc + 4, 8);
+    std::memcpy(&bc->tuples, hc + 6, 8);
+    bc->max_tuples = hc[8];
+    std::memcpy(&bc->path_total, static_cast<uint8_t*>(h_small_) + 64, 8);
+    float ms = 0; cudaEventElapsedTime(&ms, ev0_, ev1_);
+    bc->device_ms = ms;
+    if (bc->max_tuples > fst->hint_tuples) fst->hint_tuples = bc->max_tuples;
+    return cudaSuccess;
+  }
+
+  // One general left operand (drop-in single call).  Host arrays in, host path out.
+  cudaError_t run_general(DeviceFst* fst, const HostMutable& lhs, bool lhs_negative, int32_t* status,
+                          std::vector<uint32_t>* il, std::vector<uint32_t>* ol, std::vector<double>* w, double* final_w,
+                          BatchCounters* bc) {
+    *bc = BatchCounters();
+    cudaStream_t stream = 0;
+    // upload lhs as CSR in stored order
+    const uint32_t S = lhs.num_states(); const uint32_t A = (uint32_t)lhs.total_arcs();
+    std::vector<uint32_t> off(S + 1), ail(A), aol(A), anx(A); std::vector<double> aw(A), fin(S);
+    uint32_t k = 0;
+    for (uint32_t s = 0; s < S; s++) {
+      off[s] = k; fin[s] = lhs.finals[s];
+      for (const HostArc& a : lhs.arcs[s]) { ail[k] = a.ilabel; aol[k] = a.olabel; aw[k] = a.weight; anx[k] = a.nextstate; k++; }
+    }
+    off[S] = k;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    size_t o_off = 0, o_fin = o_off + al((S + 1) * 4), o_il = o_fin + al((size_t)S * 8), o_ol = o_il + al((size_t)A * 4),
+           o_w = o_ol + al((size_t)A * 4), o_nx = o_w + al((size_t)A * 8), total = o_nx + al((size_t)A * 4) + 256;
+    std::vector<uint8_t> h(total, 0);
+    std::memcpy(h.data() + o_off, off.data(), (S + 1) * 4);
+    if (S) std::memcpy(h.data() + o_fin, fin.data(), (size_t)S * 8);
+    if (A) { std::memcpy(h.data() + o_il, ail.data(), (size_t)A * 4); std::memcpy(h.data() + o_ol, aol.data(), (size_t)A * 4);
+             std::memcpy(h.data() + o_w, aw.data(), (size_t)A * 8); std::memcpy(h.data() + o_nx, anx.data(), (size_t)A * 4); }
+    uint8_t* d_lhs = nullptr;
+    FSTB_CUDA(cudaMalloc(&d_lhs, total));
+    struct Guard { uint8_t* p; ~Guard() { cudaFree(p); } } guard{d_lhs};
+    FSTB_CUDA(cudaMemcpyAsync(d_lhs, h.data(), total, cudaMemcpyHostToDevice, stream));
+    const uint64_t path_capacity = 1u << 16;
+    FSTB_CUDA(ensure_scratch(1, path_capacity));
+    uint32_t* d_cnt = static_cast<uint32_t*>(d_small_);
+    const Config cfg = global_config();
+    const bool serial = fst->serial || lhs_negative;
+    uint32_t tuple_cap = 4096;
+    FSTB_CUDA(cudaEventRecord(ev0_, stream));
+    for (;;) {
+      bc->passes++;
+      uint32_t hash_cap = 1024;
+      while ((uint64_t)hash_cap * 6 / 10 < tuple_cap && hash_cap < (1u << 31)) hash_cap <<= 1;
+      tuple_cap = (uint32_t)((uint64_t)hash_cap * 6 / 10);
+      uint32_t heap_cap = tuple_cap * 3;
+      uint64_t stride = arena_bytes(hash_cap, tuple_cap, heap_cap);
+      if (stride > workspace_budget(cfg)) { *status = kStTooLarge; return cudaSuccess; }
+      FSTB_CUDA(ensure_workspace(stride, hash_cap, tuple_cap, stride, 1, stream));
+      FSTB_CUDA(cudaMemsetAsync(d_cnt, 0, 64, stream));
+      SearchParams p{};
+      p.fst = fst->view;
+      p.n_items = 1;
+      p.lhs.num_states = S; p.lhs.num_arcs = A; p.lhs.start = lhs.start;
+      p.lhs.arc_off = reinterpret_cast<const uint32_t*>(d_lhs + o_off);
+      p.lhs.final_w = reinterpret_cast<const double*>(d_lhs + o_fin);
+      p.lhs.ilabel = reinterpret_cast<const uint32_t*>(d_lhs + o_il);
+      p.lhs.olabel = reinterpret_cast<const uint32_t*>(d_lhs + o_ol);
+      p.lhs.weight = reinterpret_cast<const double*>(d_lhs + o_w);
+      p.lhs.next = reinterpret_cast<const uint32_t*>(d_lhs + o_nx);
+      p.arena = static_cast<uint8_t*>(d_workspace_); p.arena_stride = stride;
+      p.hash_cap = hash_cap; p.tuple_cap = tuple_cap; p.heap_cap = heap_cap; p.exhaustive = cfg.exhaustive;
+      p.queue_head = d_cnt + 0;
+      p.pool_cursor = reinterpret_cast<unsigned long long*>(d_cnt + 2);
+      p.relax_counter = reinterpret_cast<unsigned long long*>(d_cnt + 4);
+      p.tuple_counter = reinterpret_cast<unsigned long long*>(d_cnt + 6);
+      p.status = d_status1_; p.path_len = d_path_len_; p.pool_off = d_pool_off_; p.final_w = d_final1_; p.n_tuples = d_out_len_;
+      p.pool = d_pool_; p.pool_cap = pool_cap_;
+      if (serial) csp_general_kernel<true><<<1, 32, 0, stream>>>(p);
+      else csp_general_kernel<false><<<1, 32, 0, stream>>>(p);
+      bc->launches++;
+      FSTB_CUDA(cudaGetLastError());
+      struct { int32_t st; uint32_t plen; double fw; } r;
+      FSTB_CUDA(cudaMemcpyAsync(&r.st, d_status1_, 4, cudaMemcpyDeviceToHost, stream));
+      FSTB_CUDA(cudaMemcpyAsync(&r.plen, d_path_len_, 4, cudaMemcpyDeviceToHost, stream));
+      FSTB_CUDA(cudaMemcpyAsync(&r.fw, d_final1_, 8, cudaMemcpyDeviceToHost, stream));
+      FSTB_CUDA(cudaMemcpyAsync(h_small_, d_cnt, 64, cudaMemcpyDeviceToHost, stream));
+      FSTB_CUDA(cudaStreamSynchronize(stream));
+      if (r.st == kStRetry) {
+        unsigned long long used; std::memcpy(&used, static_cast<uint32_t*>(h_small_) + 2, 8);
+        if (used > pool_cap_) { FSTB_CUDA(ensure_scratch(1, used * 2)); continue; }
+        if (tuple_cap > (1u << 31) / 8) { *status = kStTooLarge; return cudaSuccess; }
+        tuple_cap *= 8;
+        continue;
+      }
+      *status = r.st; *final_w = r.fw;
+      il->assign(r.plen, 0); ol->assign(r.plen, 0); w->assign(r.plen, 0.0);
+      if (r.st == kStPath && r.plen) {
+        std::vector<PoolArc> rev(r.plen);
+        FSTB_CUDA(cudaMemcpy(rev.data(), d_pool_, (size_t)r.plen * sizeof(PoolArc), cudaMemcpyDeviceToHost));   // pool_off == 0 (cursor reset)
+        for (uint32_t i = 0; i < r.plen; i++) { const PoolArc& a = rev[r.plen - 1 - i]; (*il)[i] = a.ilabel; (*ol)[i] = a.olabel; (*w)[i] = a.weight; }
+      }
+      std::memcpy(&bc->relax, static_cast<uint32_t*>(h_small_) + 4, 8);
+      std::memcpy(&bc->tuples, static_cast<uint32_t*>(h_small_) + 6, 8);
+      FSTB_CUDA(cudaEventRecord(ev1_, stream));
+      FSTB_CUDA(cudaEventSynchronize(ev1_));
+      float ms = 0; cudaEventElapsedTime(&ms, ev0_, ev1_); bc->device_ms = ms;
+      return cudaSuccess;
+    }
+  }
+
+  void release_all() {
+    cudaFree(d_workspace_); d_workspace_ = nullptr; workspace_bytes_ = 0; layout_hash_cap_ = 0;
+    free_scratch();
+  }
+
+  uint64_t pool_capacity() const { return pool_cap_; }
+
+ private:
+  void* d_small_ = nullptr; void* h_small_ = nullptr;
+  cudaEvent_t ev0_{}, ev1_{};
+  // workspace (arenas)
+  void* d_workspace_ = nullptr; uint64_t workspace_bytes_ = 0;
+  uint32_t layout_hash_cap_ = 0, layout_tuple_cap_ = 0, layout_groups_ = 0; uint64_t layout_stride_ = 0;
+  // per-batch scratch
+  uint32_t scratch_n_ = 0;
+  uint32_t* d_path_len_ = nullptr; uint64_t* d_pool_off_ = nullptr; uint32_t* d_out_len_ = nullptr; uint64_t* d_len64_ = nullptr;
+  uint32_t* d_order_buf_[2] = {nullptr, nullptr};
+  int32_t* d_status1_ = nullptr; double* d_final1_ = nullptr;
+  PoolArc* d_pool_ = nullptr; uint64_t pool_cap_ = 0;
+  void* d_scan_tmp_ = nullptr; size_t scan_tmp_bytes_ = 0;
+
+  static uint32_t choose_lanes(const Config& cfg, const DeviceFst* fst) {
+    uint32_t g = cfg.lanes_per_string;
+    if (g == 32 || g == 16 || g == 8 || g == 4) return g;
+    uint32_t d = fst->view.max_degree;
+    if (d > 16) return 32;
+    if (d > 8) return 16;
+    return 8;
+  }
+
+  uint32_t max_resident_groups(uint32_t G, bool serial) {
+    int bps = 0;
+    const void* fn = kernel_ptr(G, serial);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, 128, 0) != cudaSuccess || bps <= 0) bps = 4;
+    return (uint32_t)bps * (uint32_t)sm_count * (128 / G);
+  }
+  static const void* kernel_ptr(uint32_t G, bool serial) {
+    if (serial) {
+      switch (G) { case 32: return (const void*)csp_batch_kernel<32, true>; case 16: return (const void*)csp_batch_kernel<16, true>;
+                   case 8: return (const void*)csp_batch_kernel<8, true>; default: return (const void*)csp_batch_kernel<4, true>; }
+    }
+    switch (G) { case 32: return (const void*)csp_batch_kernel<32, false>; case 16: return (const void*)csp_batch_kernel<16, false>;
+                 case 8: return (const void*)csp_batch_kernel<8, false>; default: return (const void*)csp_batch_kernel<4, false>; }
+  }
+  static void launch_search(uint32_t G, bool serial, uint32_t blocks, uint32_t threads, const SearchParams& p, cudaStream_t s) {
+    if (serial) {
+      switch (G) { case 32: csp_batch_kernel<32, true><<<blocks, threads, 0, s>>>(p); break; case 16: csp_batch_kernel<16, true><<<blocks, threads, 0, s>>>(p); break;
+                   case 8: csp_batch_kernel<8, true><<<blocks, threads, 0, s>>>(p); break; default: csp_batch_kernel<4, true><<<blocks, threads, 0, s>>>(p); break; }
+    } else {
+      switch (G) { case 32: csp_batch_kernel<32, false><<<blocks, threads, 0, s>>>(p); break; case 16: csp_batch_kernel<16, false><<<blocks, threads, 0, s>>>(p); break;
+                   case 8: csp_batch_kernel<8, false><<<blocks, threads, 0, s>>>(p); break; default: csp_batch_kernel<4, false><<<blocks, threads, 0, s>>>(p); break; }
+    }
+  }
+
+  uint64_t workspace_budget(const Config& cfg) {
+    if (cfg.workspace_bytes) return cfg.workspace_bytes;
+    if (budget_cache_) return budget_cache_;
+    size_t fr = 0, tot = 0;
+    if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) return 1ull << 30;
+    budget_cache_ = (uint64_t)((fr + workspace_bytes_) * 0.6);
+    return budget_cache_;
+  }
+  uint64_t budget_cache_ = 0;
+
+  cudaError_t ensure_workspace(uint64_t bytes, uint32_t hash_cap, uint32_t tuple_cap, uint64_t stride, uint32_t groups, cudaStream_t s) {
+    if (bytes > workspace_bytes_) {
+      if (d_workspace_) { FSTB_CUDA(cudaStreamSynchronize(s)); FSTB_CUDA(cudaFree(d_workspace_)); d_workspace_ = nullptr; workspace_bytes_ = 0; }
+      FSTB_CUDA(cudaMalloc(&d_workspace_, bytes));
+      workspace_bytes_ = bytes;
+      layout_hash_cap_ = 0;
+    }
+    // table keys must be all-ones (empty) under the layout in use; kernels leave
+    // their tables empty, so a memset is needed only when the layout changes.
+    if (hash_cap != layout_hash_cap_ || tuple_cap != layout_tuple_cap_ || stride != layout_stride_ || groups > layout_groups_) {
+      FSTB_CUDA(cudaMemsetAsync(d_workspace_, 0xFF, bytes, s));
+      layout_hash_cap_ = hash_cap; layout_tuple_cap_ = tuple_cap; layout_stride_ = stride; layout_groups_ = groups;
+    }
+    return cudaSuccess;
+  }
+
+  void free_scratch() {
+    cudaFree(d_path_len_); cudaFree(d_pool_off_); cudaFree(d_out_len_); cudaFree(d_len64_); cudaFree(d_order_buf_[0]); cudaFree(d_order_buf_[1]);
+    cudaFree(d_status1_); cudaFree(d_final1_); cudaFree(d_pool_); cudaFree(d_scan_tmp_);
+    d_path_len_ = nullptr; d_pool_off_ = nullptr; d_out_len_ = nullptr; d_len64_ = nullptr; d_order_buf_[0] = d_order_buf_[1] = nullptr;
+    d_status1_ = nullptr; d_final1_ = nullptr; d_pool_ = nullptr; d_scan_tmp_ = nullptr; scratch_n_ = 0; pool_cap_ = 0; scan_tmp_bytes_ = 0;
+  }
+  cudaError_t ensure_scratch(uint32_t n, uint64_t pool_cap) {
+    if (n > scratch_n_) {
+      cudaFree(d_path_len_); cudaFree(d_pool_off_); cudaFree(d_out_len_); cudaFree(d_len64_); cudaFree(d_order_buf_[0]); cudaFree(d_order_buf_[1]);
+      cudaFree(d_status1_); cudaFree(d_final1_); cudaFree(d_scan_tmp_);
+      uint32_t m = n + n / 8 + 16;
+      FSTB_CUDA(cudaMalloc(&d_path_len_, (size_t)m * 4)); FSTB_CUDA(cudaMalloc(&d_pool_off_, (size_t)m * 8));
+      FSTB_CUDA(cudaMalloc(&d_out_len_, (size_t)m * 4)); FSTB_CUDA(cudaMalloc(&d_len64_, (size_t)(m + 1) * 8));
+      FSTB_CUDA(cudaMalloc(&d_order_buf_[0], (size_t)m * 4)); FSTB_CUDA(cudaMalloc(&d_order_buf_[1], (size_t)m * 4));
+      FSTB_CUDA(cudaMalloc(&d_status1_, 16)); FSTB_CUDA(cudaMalloc(&d_final1_, 16));
+      size_t tmp = 0;
+      FSTB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, (uint64_t*)nullptr, (uint64_t*)nullptr, (int)(m + 1)));
+      FSTB_CUDA(cudaMalloc(&d_scan_tmp_, tmp + 256));
+      scan_tmp_bytes_ = tmp + 256;
+      scratch_n_ = m;
+    }
+    if (pool_cap > pool_cap_) {
+      cudaFree(d_pool_);
+      FSTB_CUDA(cudaMalloc(&d_pool_, (size_t)pool_cap * sizeof(PoolArc)));
+      pool_cap_ = pool_cap;
+    }
+    return cudaSuccess;
+  }
+};
+
+}  // namespace fstb200
