@@ -1,0 +1,311 @@
+#!/usr/bin/env python3
+"""bench.py — batched compose_shortest_path throughput on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA engine
+    python bench.py --impl reference --gpus N --steps K ...   # CPU arm: oracle port of the reference, all host cores
+
+One "step" = one pass of the hot path over one batch of synthetic strings of the
+headline workload (BASELINE.json configs[1]): scenario
+compose_frozen_lazy_shortest_path_epsilon_dense, len 96, transducer-len 4096,
+branches 12.  The literal 1 M-string batch is processed as consecutive steps of
+`--batch` strings per GPU (throughput is per string; the batch actually run is in
+the JSON).  Weak scaling: every rank searches its own `--batch` strings against
+its own replica of the transducer; there is no collective on the data path.
+
+`value` : strings/s with inputs and outputs resident in HBM (fst_b200_batch_device).
+`e2e`   : strings/s through fst_compose_frozen_shortest_path_batch with HOST buffers
+          (H2D of the strings and D2H of the paths inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {"epsilon_dense": 1, "ambiguous": 2, "plain": 0}   # name -> oracle generator kind (CPU arm only)
+SCENARIO = {"epsilon_dense": "compose_frozen_lazy_shortest_path_epsilon_dense",
+            "ambiguous": "compose_frozen_lazy_shortest_path_ambiguous",
+            "plain": "compose_frozen_lazy_shortest_path"}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="epsilon_dense", choices=sorted(WORKLOADS))
+    ap.add_argument("--len", type=int, default=96)
+    ap.add_argument("--transducer-len", type=int, default=4096)
+    ap.add_argument("--branches", type=int, default=12)
+    ap.add_argument("--batch", type=int, default=0, help="strings per GPU per step (0 = workload default)")
+    ap.add_argument("--lanes", type=int, default=0)
+    ap.add_argument("--exhaustive", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="strings in the CPU baseline sample (0 = auto)")
+    return ap.parse_args()
+
+
+DEFAULT_BATCH = {"epsilon_dense": 4096, "ambiguous": 65536, "plain": 1 << 20}
+
+
+def input_string(workload: str, length: int, branches: int) -> bytes:
+    if workload == "plain":
+        return bytes(i % max(1, branches) for i in range(length))
+    return bytes(length)
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks/throttle reasons while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[0])); mx = max(mx, float(s[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def run_reference(args):
+    """CPU arm: the oracle port of the reference's composeShortestPath on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    f = oracle.Frozen.generate(WORKLOADS[args.workload], args.transducer_len, args.branches)
+    s = input_string(args.workload, args.len, args.branches)
+    cores = os.cpu_count() or 1
+    # bounded sample per step: a few seconds of work on all cores
+    t0 = time.time(); p1 = oracle.csp_bytes(f, s); one = max(time.time() - t0, 1e-6)
+    R1 = p1.relax_calls
+    sample = args.cpu_sample or int(max(cores, min(cores * 64, cores * max(1.0, 5.0 / one))))
+    data = np.frombuffer(s * sample, np.uint8)
+    offsets = (np.arange(sample + 1, dtype=np.uint64) * len(s))
+    for _ in range(args.warmup):
+        oracle.csp_batch_bytes(f, data, offsets, n_threads=cores)
+    secs = 0.0
+    for _ in range(args.steps):
+        secs += oracle.csp_batch_bytes(f, data, offsets, n_threads=cores)["seconds"]
+    ms = secs / args.steps * 1e3
+    v = sample / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": "strings/sec batched compose_shortest_path", "value": v, "unit": "strings/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, sample, 0),
+        "composed_arcs_per_sec": v * R1,
+        "cpu_baseline": {"value": v, "unit": "strings/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} strings/step of the same workload, {cores} threads, C++ restatement of the reference "
+                                   f"(zig toolchain absent; oracle/fst_oracle.hpp)"},
+        "e2e": {"value": v, "unit": "strings/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, batch, state_bytes):
+    return {"workload": f"{SCENARIO[args.workload]} len={args.len} transducer_len={args.transducer_len} branches={args.branches}",
+            "batch_per_gpu_per_step": batch, "literal_batch": 1000000,
+            "cache": f"inputs+search state >> L2 (per-step search state ~{state_bytes / 2**30:.1f} GiB in HBM); no L2 flush needed",
+            "lanes_per_string": args.lanes or "auto", "exhaustive": args.exhaustive}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import libfst_b200 as L
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the b200 arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L.load()
+    L.configure(lanes_per_string=args.lanes, exhaustive=args.exhaustive)
+
+    from libfst_b200 import synth
+    fst = synth.TRANSDUCERS[args.workload](args.transducer_len, args.branches).freeze()
+    s = input_string(args.workload, args.len, args.branches)
+    batch = args.batch or DEFAULT_BATCH[args.workload]
+
+    # ── device-resident inputs/outputs (torch owns the memory; the library gets raw pointers) ──
+    dev = torch.device("cuda", local)
+    h_bytes = torch.frombuffer(bytearray(s * batch), dtype=torch.uint8).pin_memory() if len(s) else torch.zeros(1, dtype=torch.uint8).pin_memory()
+    h_off = (torch.arange(batch + 1, dtype=torch.int64) * len(s)).pin_memory()
+    d_bytes, d_off = h_bytes.to(dev), h_off.to(dev)
+    cap = batch * (2 * args.len + 32) + 1024
+    d_status = torch.empty(batch, dtype=torch.int32, device=dev)
+    d_poff = torch.empty(batch + 1, dtype=torch.int64, device=dev)
+    d_il = torch.empty(cap, dtype=torch.int32, device=dev)
+    d_ol = torch.empty(cap, dtype=torch.int32, device=dev)
+    d_w = torch.empty(cap, dtype=torch.float64, device=dev)
+    d_fin = torch.empty(batch, dtype=torch.float64, device=dev)
+    d_nt = torch.empty(batch, dtype=torch.int32, device=dev)
+    out = L.DeviceOut(d_status.data_ptr(), d_poff.data_ptr(), d_il.data_ptr(), d_ol.data_ptr(), d_w.data_ptr(), d_fin.data_ptr(),
+                      d_nt.data_ptr(), cap)
+    stream = torch.cuda.current_stream()
+
+    def step_device():
+        rc = L.lib().fst_b200_batch_device(fst.h, d_bytes.data_ptr(), d_off.data_ptr(), batch, len(s), C.byref(out), stream.cuda_stream)
+        if rc != 0:
+            raise RuntimeError(f"fst_b200_batch_device failed: FstError {rc}")
+        return L.last_counters()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches, relax, kernel_ms = 0, 0, 0.0
+    ev0.record(stream)
+    for _ in range(args.steps):
+        c = step_device()
+        launches += c["launches"]; relax += c["relaxations"]; kernel_ms += c["device_ms"]
+    ev1.record(stream)
+    barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    sampler.stop_flag.set(); sampler.join(timeout=2)
+    # correctness of what was timed: every string must have the reference's path length and total
+    st = d_status.cpu().numpy(); poff = d_poff.cpu().numpy()
+    assert (st == 0).all(), "bench: a string did not produce a path"
+    plens = np.diff(poff)
+    P1 = int(plens[0])
+    assert (plens == P1).all(), "bench: identical strings produced different path lengths"
+    path0 = (d_il[:P1].cpu().numpy().astype(np.uint32), d_ol[:P1].cpu().numpy().astype(np.uint32), d_w[:P1].cpu().numpy())
+    tuples_per_string = float(d_nt.float().mean().item())
+
+    # ── end to end through the host-buffer C ABI ──
+    e2e = None
+    if not args.no_e2e:
+        hb, ho = h_bytes.numpy(), h_off.numpy().astype(np.uint64)
+        for _ in range(1):
+            L.compose_frozen_shortest_path_batch(fst, hb, ho)
+        barrier()
+        t0 = time.perf_counter()
+        d2h = 0
+        for _ in range(args.steps):
+            r = L.compose_frozen_shortest_path_batch(fst, hb, ho)
+            d2h = (r.status.nbytes + r.path_offsets.nbytes + r.ilabels.nbytes + r.olabels.nbytes + r.weights.nbytes +
+                   r.final_weights.nbytes + r.n_tuples.nbytes + r.out_offsets.nbytes + r.out_bytes.nbytes)
+        torch.cuda.synchronize()
+        e2e_ms = (time.perf_counter() - t0) * 1e3
+        e2e = {"ms": e2e_ms, "h2d": int(hb.nbytes + ho.nbytes), "d2h": int(d2h)}
+
+    # ── max over ranks ──
+    if dist is not None:
+        t = torch.tensor([elapsed_ms, kernel_ms, e2e["ms"] if e2e else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms, kernel_ms = float(t[0]), float(t[1])
+        if e2e:
+            e2e["ms"] = float(t[2])
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    total_strings = batch * world * args.steps
+    value = total_strings / (elapsed_ms / 1e3)
+    ms_per_step = elapsed_ms / args.steps
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    # algorithmic bytes per string: 20 B per relaxation (one SoA arc record), 16 B per tuple
+    # (dist + back-pointer), 4 B per input label, 16 B per emitted path arc — from the counters of the run itself
+    relax_per_string = relax / (batch * args.steps)
+    alg_bytes = 20.0 * relax_per_string + 16.0 * tuples_per_string + 4.0 * args.len + 16.0 * P1
+    per_launch_bytes = alg_bytes * batch
+    kernel_ms_per_launch = kernel_ms / args.steps
+    achieved = per_launch_bytes / (kernel_ms_per_launch / 1e3) / 1e9
+    line = {
+        "metric": "strings/sec batched compose_shortest_path", "value": value, "unit": "strings/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, batch, tuples_per_string * 90 * min(batch, 4096)),
+        "composed_arcs_per_sec": value * relax_per_string,
+        "work_per_string": {"path_arcs": P1, "tuples_run": tuples_per_string, "relax_run": relax_per_string},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "kernel": "csp_batch_kernel",
+                     "alg_bytes_per_string": alg_bytes, "kernel_ms_per_launch": kernel_ms_per_launch},
+        "gpu_launches": launches,
+        "clocks": sampler.summary(),
+    }
+    if e2e:
+        line["e2e"] = {"value": total_strings / (e2e["ms"] / 1e3), "unit": "strings/s", "h2d_bytes_per_step": e2e["h2d"],
+                       "d2h_bytes_per_step": e2e["d2h"]}
+    if not args.no_cpu_baseline:
+        import oracle   # checker + CPU baseline leg only
+        f = oracle.Frozen.generate(WORKLOADS[args.workload], args.transducer_len, args.branches)
+        cores = os.cpu_count() or 1
+        t0 = time.time(); p1 = oracle.csp_bytes(f, s); one = max(time.time() - t0, 1e-6)
+        # the timed GPU result must be the oracle's path, bit for bit
+        assert np.array_equal(path0[0], p1.ilabels) and np.array_equal(path0[1], p1.olabels) and \
+            np.array_equal(path0[2].view(np.uint64), p1.weights.view(np.uint64)), "bench: GPU path differs from the oracle"
+        line["work_per_string"].update({"tuples_ref": p1.tuples, "relax_ref": p1.relax_calls})
+        sample = args.cpu_sample or int(max(cores, min(cores * 64, cores * max(1.0, 10.0 / one))))
+        data = np.frombuffer(s * sample, np.uint8)
+        offsets = np.arange(sample + 1, dtype=np.uint64) * len(s)
+        secs = oracle.csp_batch_bytes(f, data, offsets, n_threads=cores)["seconds"]
+        line["cpu_baseline"] = {"value": sample / secs, "unit": "strings/s", "cores": cores, "kind": "port",
+                                "sample": f"{sample} strings of the same workload on {cores} threads ({secs:.1f} s); C++ restatement "
+                                          f"of the reference (zig toolchain absent)"}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

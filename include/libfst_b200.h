@@ -170,6 +170,14 @@ FstError fst_b200_batch_device(FstHandle b, const uint8_t* d_bytes, const uint64
                                uint32_t n_strings, uint32_t max_len, const FstB200DeviceOut* out,
                                void* stream);
 
+/* Bulk builders: same effect (and error codes) as repeated fst_mutable_add_state /
+ * fst_mutable_set_final / fst_mutable_add_arc, under one lock.  Arcs are appended
+ * to their source state in array order. */
+FstError fst_b200_mutable_add_states(FstMutableHandle handle, uint32_t n);
+FstError fst_b200_mutable_set_finals(FstMutableHandle handle, uint32_t n, const uint32_t* states, const double* weights);
+FstError fst_b200_mutable_add_arcs(FstMutableHandle handle, uint64_t n, const uint32_t* src, const uint32_t* ilabel,
+                                   const uint32_t* olabel, const double* weight, const uint32_t* nextstate);
+
 /* Tuning / introspection (all optional). */
 typedef struct {
   uint64_t workspace_bytes;   /* device budget for search state; 0 = 60% of free HBM     */

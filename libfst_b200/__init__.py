@@ -80,6 +80,9 @@ EXPORTS = {
     "fst_b200_batch_free": (None, [C.POINTER(_BatchResult)]),
     "fst_b200_batch_device": (C.c_int, [C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
                                         C.POINTER(DeviceOut), C.c_void_p]),
+    "fst_b200_mutable_add_states": (C.c_int, [C.c_uint64, C.c_uint32]),
+    "fst_b200_mutable_set_finals": (C.c_int, [C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "fst_b200_mutable_add_arcs": (C.c_int, [C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fst_b200_configure": (C.c_int, [C.POINTER(Config)]),
     "fst_b200_last_counters": (None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
     "fst_b200_device_count": (C.c_int32, []),
@@ -148,9 +151,19 @@ class MutableFst:
         self.h = FST_INVALID_HANDLE
 
     def add_state(self): return lib().fst_mutable_add_state(self.h)
-    def add_states(self, n):
-        for _ in range(n): self.add_state()
+    def add_states(self, n): return lib().fst_b200_mutable_add_states(self.h, n)
     def set_start(self, s): return lib().fst_mutable_set_start(self.h, s)
+
+    def set_finals(self, states, weights):
+        st = np.ascontiguousarray(states, np.uint32); w = np.ascontiguousarray(weights, np.float64)
+        return lib().fst_b200_mutable_set_finals(self.h, len(st), st.ctypes.data, w.ctypes.data)
+
+    def add_arcs(self, src, il, ol, w, nxt):
+        src, il, ol, nxt = (np.ascontiguousarray(x, np.uint32) for x in (src, il, ol, nxt))
+        w = np.ascontiguousarray(w, np.float64)
+        return lib().fst_b200_mutable_add_arcs(self.h, len(src), src.ctypes.data, il.ctypes.data, ol.ctypes.data,
+                                                w.ctypes.data, nxt.ctypes.data)
+
     def set_final(self, s, w=0.0): return lib().fst_mutable_set_final(self.h, s, float(w))
     def add_arc(self, src, il, ol, w, nxt): return lib().fst_mutable_add_arc(self.h, src, il, ol, float(w), nxt)
     def start(self): return lib().fst_mutable_start(self.h)

@@ -203,6 +203,32 @@ FstError fst_mutable_add_arc(FstMutableHandle handle, uint32_t src, uint32_t ila
   return FST_OK;
 }
 
+// Bulk builders (new; same effect as the per-call builders above, one lock).
+FstError fst_b200_mutable_add_states(FstMutableHandle handle, uint32_t n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  HostMutable* m = g_mutables.get(handle);
+  if (!m) return FST_INVALID_ARG;
+  m->add_states(n);
+  return FST_OK;
+}
+FstError fst_b200_mutable_set_finals(FstMutableHandle handle, uint32_t n, const uint32_t* states, const double* weights) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  HostMutable* m = g_mutables.get(handle);
+  if (!m || (n && (!states || !weights))) return FST_INVALID_ARG;
+  for (uint32_t i = 0; i < n; i++) if (states[i] >= m->num_states()) return FST_INVALID_STATE;
+  for (uint32_t i = 0; i < n; i++) m->finals[states[i]] = weights[i];
+  return FST_OK;
+}
+FstError fst_b200_mutable_add_arcs(FstMutableHandle handle, uint64_t n, const uint32_t* src, const uint32_t* ilabel,
+                                   const uint32_t* olabel, const double* weight, const uint32_t* nextstate) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  HostMutable* m = g_mutables.get(handle);
+  if (!m || (n && (!src || !ilabel || !olabel || !weight || !nextstate))) return FST_INVALID_ARG;
+  for (uint64_t i = 0; i < n; i++) if (src[i] >= m->num_states() || nextstate[i] >= m->num_states()) return FST_INVALID_STATE;
+  for (uint64_t i = 0; i < n; i++) m->arcs[src[i]].push_back(HostArc{ilabel[i], olabel[i], weight[i], nextstate[i]});
+  return FST_OK;
+}
+
 // ── mutable queries (src/c-api.zig:1376-1424) ──
 uint32_t fst_mutable_start(FstMutableHandle handle) {
   std::lock_guard<std::mutex> lk(g_mu);

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "csp_kernels.cuh"
+#include "csp_fast.cuh"
 #include "host_fst.hpp"
 
 namespace fstb200 {
@@ -184,11 +185,14 @@ class Engine {
     const uint32_t* d_order = nullptr;
     for (uint32_t pass = 0;; pass++) {
       bc->passes++;
-      uint32_t hash_cap = 1024;
-      while ((uint64_t)hash_cap * 6 / 10 < tuple_cap && hash_cap < (1u << 31)) hash_cap <<= 1;
-      tuple_cap = (uint32_t)((uint64_t)hash_cap * 6 / 10);
-      uint32_t heap_cap = tuple_cap * 3;
-      uint64_t stride = arena_bytes(hash_cap, tuple_cap, heap_cap);
+      uint32_t hash_cap, heap_cap; uint64_t stride;
+      const bool fast = !fst->serial;
+      if (fast && tuple_cap > kMaxFastTuples) {
+        mark_too_large_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_status, d_path_len_, n);
+        bc->launches++;
+        break;
+      }
+      layout_for(fast, tuple_cap, hash_cap, heap_cap, stride);
       uint32_t max_groups = max_resident_groups(G, fst->serial);
       uint32_t want = std::min<uint32_t>(n_items, max_groups);
       uint64_t ws = workspace_budget(cfg);
@@ -206,7 +210,8 @@ class Engine {
       } else {
         blocks = 1; gpb = std::min(want, fit); threads = gpb * G;
       }
-      FSTB_CUDA(ensure_workspace((uint64_t)blocks * gpb * stride, hash_cap, tuple_cap, stride, blocks * gpb, stream));
+      FSTB_CUDA(ensure_workspace((uint64_t)blocks * gpb * stride, fast, hash_cap, tuple_cap, heap_cap, stride, blocks * gpb, stream));
+      bc->launches += init_launches_; init_launches_ = 0;
 
       SearchParams p{};
       p.fst = fst->view;
@@ -321,13 +326,13 @@ class Engine {
     FSTB_CUDA(cudaEventRecord(ev0_, stream));
     for (;;) {
       bc->passes++;
-      uint32_t hash_cap = 1024;
-      while ((uint64_t)hash_cap * 6 / 10 < tuple_cap && hash_cap < (1u << 31)) hash_cap <<= 1;
-      tuple_cap = (uint32_t)((uint64_t)hash_cap * 6 / 10);
-      uint32_t heap_cap = tuple_cap * 3;
-      uint64_t stride = arena_bytes(hash_cap, tuple_cap, heap_cap);
+      uint32_t hash_cap, heap_cap; uint64_t stride;
+      const bool fast = !serial;
+      if (fast && tuple_cap > kMaxFastTuples) { *status = kStTooLarge; return cudaSuccess; }
+      layout_for(fast, tuple_cap, hash_cap, heap_cap, stride);
       if (stride > workspace_budget(cfg)) { *status = kStTooLarge; return cudaSuccess; }
-      FSTB_CUDA(ensure_workspace(stride, hash_cap, tuple_cap, stride, 1, stream));
+      FSTB_CUDA(ensure_workspace(stride, fast, hash_cap, tuple_cap, heap_cap, stride, 1, stream));
+      bc->launches += init_launches_; init_launches_ = 0;
       FSTB_CUDA(cudaMemsetAsync(d_cnt, 0, 64, stream));
       SearchParams p{};
       p.fst = fst->view;
@@ -348,7 +353,7 @@ class Engine {
       p.status = d_status1_; p.path_len = d_path_len_; p.pool_off = d_pool_off_; p.final_w = d_final1_; p.n_tuples = d_out_len_;
       p.pool = d_pool_; p.pool_cap = pool_cap_;
       if (serial) csp_general_kernel<true><<<1, 32, 0, stream>>>(p);
-      else csp_general_kernel<false><<<1, 32, 0, stream>>>(p);
+      else csp_general_fast_kernel<<<1, 32, 0, stream>>>(p);
       bc->launches++;
       FSTB_CUDA(cudaGetLastError());
       struct { int32_t st; uint32_t plen; double fw; } r;
@@ -401,6 +406,25 @@ class Engine {
   PoolArc* d_pool_ = nullptr; uint64_t pool_cap_ = 0;
   void* d_scan_tmp_ = nullptr; size_t scan_tmp_bytes_ = 0;
 
+  uint32_t init_launches_ = 0;
+  bool layout_fast_ = false; uint32_t layout_heap_cap_ = 0;
+
+  // arena geometry for a per-string tuple capacity
+  static void layout_for(bool fast, uint32_t& tuple_cap, uint32_t& hash_cap, uint32_t& heap_cap, uint64_t& stride) {
+    if (fast) {
+      if (tuple_cap < 256) tuple_cap = 256;
+      hash_cap = (uint32_t)std::min<uint64_t>(0xFFFFFFF0ull, (uint64_t)tuple_cap * 100 / 65 + 16);
+      heap_cap = 96 + tuple_cap / 12;     // 128-byte chunks of 31 ids: ~2.6 queued ids per tuple
+      stride = fast_layout(hash_cap, tuple_cap, heap_cap).total;
+    } else {
+      hash_cap = 1024;
+      while ((uint64_t)hash_cap * 6 / 10 < tuple_cap && hash_cap < (1u << 31)) hash_cap <<= 1;
+      tuple_cap = (uint32_t)((uint64_t)hash_cap * 6 / 10);
+      heap_cap = tuple_cap * 3;
+      stride = arena_bytes(hash_cap, tuple_cap, heap_cap);
+    }
+  }
+
   static uint32_t choose_lanes(const Config& cfg, const DeviceFst* fst) {
     uint32_t g = cfg.lanes_per_string;
     if (g == 32 || g == 16 || g == 8 || g == 4) return g;
@@ -413,7 +437,7 @@ class Engine {
   uint32_t max_resident_groups(uint32_t G, bool serial) {
     int bps = 0;
     const void* fn = kernel_ptr(G, serial);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, 128, 0) != cudaSuccess || bps <= 0) bps = 4;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, 128, serial ? 0 : (128 / G) * 64 * sizeof(uint2)) != cudaSuccess || bps <= 0) bps = 4;
     return (uint32_t)bps * (uint32_t)sm_count * (128 / G);
   }
   static const void* kernel_ptr(uint32_t G, bool serial) {
@@ -421,16 +445,17 @@ class Engine {
       switch (G) { case 32: return (const void*)csp_batch_kernel<32, true>; case 16: return (const void*)csp_batch_kernel<16, true>;
                    case 8: return (const void*)csp_batch_kernel<8, true>; default: return (const void*)csp_batch_kernel<4, true>; }
     }
-    switch (G) { case 32: return (const void*)csp_batch_kernel<32, false>; case 16: return (const void*)csp_batch_kernel<16, false>;
-                 case 8: return (const void*)csp_batch_kernel<8, false>; default: return (const void*)csp_batch_kernel<4, false>; }
+    switch (G) { case 32: return (const void*)csp_batch_fast_kernel<32>; case 16: return (const void*)csp_batch_fast_kernel<16>;
+                 case 8: return (const void*)csp_batch_fast_kernel<8>; default: return (const void*)csp_batch_fast_kernel<4>; }
   }
   static void launch_search(uint32_t G, bool serial, uint32_t blocks, uint32_t threads, const SearchParams& p, cudaStream_t s) {
     if (serial) {
       switch (G) { case 32: csp_batch_kernel<32, true><<<blocks, threads, 0, s>>>(p); break; case 16: csp_batch_kernel<16, true><<<blocks, threads, 0, s>>>(p); break;
                    case 8: csp_batch_kernel<8, true><<<blocks, threads, 0, s>>>(p); break; default: csp_batch_kernel<4, true><<<blocks, threads, 0, s>>>(p); break; }
     } else {
-      switch (G) { case 32: csp_batch_kernel<32, false><<<blocks, threads, 0, s>>>(p); break; case 16: csp_batch_kernel<16, false><<<blocks, threads, 0, s>>>(p); break;
-                   case 8: csp_batch_kernel<8, false><<<blocks, threads, 0, s>>>(p); break; default: csp_batch_kernel<4, false><<<blocks, threads, 0, s>>>(p); break; }
+      const size_t sm = (size_t)(threads / G) * 64 * sizeof(uint2);
+      switch (G) { case 32: csp_batch_fast_kernel<32><<<blocks, threads, sm, s>>>(p); break; case 16: csp_batch_fast_kernel<16><<<blocks, threads, sm, s>>>(p); break;
+                   case 8: csp_batch_fast_kernel<8><<<blocks, threads, sm, s>>>(p); break; default: csp_batch_fast_kernel<4><<<blocks, threads, sm, s>>>(p); break; }
     }
   }
 
@@ -444,18 +469,29 @@ class Engine {
   }
   uint64_t budget_cache_ = 0;
 
-  cudaError_t ensure_workspace(uint64_t bytes, uint32_t hash_cap, uint32_t tuple_cap, uint64_t stride, uint32_t groups, cudaStream_t s) {
+  cudaError_t ensure_workspace(uint64_t bytes, bool fast, uint32_t hash_cap, uint32_t tuple_cap, uint32_t heap_cap, uint64_t stride,
+                               uint32_t groups, cudaStream_t s) {
     if (bytes > workspace_bytes_) {
       if (d_workspace_) { FSTB_CUDA(cudaStreamSynchronize(s)); FSTB_CUDA(cudaFree(d_workspace_)); d_workspace_ = nullptr; workspace_bytes_ = 0; }
       FSTB_CUDA(cudaMalloc(&d_workspace_, bytes));
       workspace_bytes_ = bytes;
       layout_hash_cap_ = 0;
     }
-    // table keys must be all-ones (empty) under the layout in use; kernels leave
-    // their tables empty, so a memset is needed only when the layout changes.
-    if (hash_cap != layout_hash_cap_ || tuple_cap != layout_tuple_cap_ || stride != layout_stride_ || groups > layout_groups_) {
-      FSTB_CUDA(cudaMemsetAsync(d_workspace_, 0xFF, bytes, s));
-      layout_hash_cap_ = hash_cap; layout_tuple_cap_ = tuple_cap; layout_stride_ = stride; layout_groups_ = groups;
+    // Arena invariants (table keys empty, ready bitmap zero) hold after every kernel for
+    // the layout in use; re-initialise only when the layout changes.
+    if (fast != layout_fast_ || hash_cap != layout_hash_cap_ || tuple_cap != layout_tuple_cap_ || heap_cap != layout_heap_cap_ ||
+        stride != layout_stride_ || groups > layout_groups_) {
+      if (fast) {
+        uint64_t words = ((uint64_t)hash_cap * 4 + tuple_cap / 60 + 64) * groups;
+        uint32_t blocks = (uint32_t)std::min<uint64_t>((words + 255) / 256, (uint64_t)sm_count * 32);
+        fast_arena_init_kernel<<<blocks, 256, 0, s>>>(static_cast<uint8_t*>(d_workspace_), stride, groups, hash_cap, tuple_cap, heap_cap);
+        init_launches_++;
+        FSTB_CUDA(cudaGetLastError());
+      } else {
+        FSTB_CUDA(cudaMemsetAsync(d_workspace_, 0xFF, bytes, s));
+      }
+      layout_fast_ = fast; layout_hash_cap_ = hash_cap; layout_tuple_cap_ = tuple_cap; layout_heap_cap_ = heap_cap;
+      layout_stride_ = stride; layout_groups_ = groups;
     }
     return cudaSuccess;
   }
