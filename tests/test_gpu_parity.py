@@ -152,3 +152,104 @@ def test_retry_passes_small_workspace(L, O, gpu):
         assert res.passes >= 2
     finally:
         L.configure()
+
+
+def test_reference_kats_on_gpu(L, O, gpu):
+    # rewrite.zig:244-498 KAT strings through the batched entry and the single-call drop-in
+    import refkat
+    for name, rule, cases in refkat.rewrite_kats():
+        spec = rule.to_spec()
+        fprod, forc, _ = frozen_pair(L, O, spec)
+        strings = [c[0] for c in cases]
+        res = assert_batch_matches_oracle(L, O, fprod, forc, strings)
+        for i, (inp, want) in enumerate(cases):
+            assert res.output(i) == want, (name, inp)
+            r = L.compose_frozen_shortest_path(L.MutableFst.compile_string(inp), fprod, 1)
+            assert r.print_string(True) == want and r.print_string(False) == inp
+
+
+def test_golden_fixtures_on_gpu(L, O, gpu):
+    import json
+    import os
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    fx = json.load(open(os.path.join(gold, "fuzz_paths.json")))
+    for case in fx["cases"]:
+        spec = Spec(case["num_states"], 0, case["finals"], [tuple(a) for a in case["arcs"]])
+        fprod = spec.to_product(L).freeze()
+        strings = [bytes.fromhex(h) for h in case["strings"]]
+        data, offsets = L.pack_strings(strings)
+        res = L.compose_frozen_shortest_path_batch(fprod, data, offsets)
+        for i, want in enumerate(case["paths"]):
+            if want is None:
+                assert res.status[i] != L.PATH
+                continue
+            il, ol, w = res.path(i)
+            assert [il.tolist(), ol.tolist(), w.tolist(), float(res.final_weights[i])] == want, (case["seed"], i)
+    import hashlib
+    fx = json.load(open(os.path.join(gold, "bench_signatures.json")))
+    from libfst_b200 import synth
+    names = {0: "plain", 1: "epsilon_dense", 2: "ambiguous"}
+    for row in fx["rows"]:
+        if row["kind"] == 1 and row["L"] > 33:
+            continue
+        f = synth.TRANSDUCERS[names[row["kind"]]](row["T"], row["B"]).freeze()
+        s = synth.input_string(names[row["kind"]], row["L"], row["B"])
+        data, offsets = L.pack_strings([s])
+        res = L.compose_frozen_shortest_path_batch(f, data, offsets)
+        il, ol, w = res.path(0)
+        sig = hashlib.sha256(";".join(f"{int(a)},{int(b)},{float(c)!r}" for a, b, c in zip(il, ol, w)).encode()).hexdigest()[:16]
+        assert sig == row["sha16"] and len(il) == row["P"] and res.total(0) == row["total"], row
+
+
+def test_mixed_lengths_large(L, O, gpu):
+    # issue-#1 profile matrix lengths (run_issue1_profile_bench.py:24-25) in ONE batch: exercises retry passes + ordering
+    img = gen_image(O, 2, 4096, 12)
+    forc, fprod = O.Frozen.from_bytes(img), L.Fst.from_image(img)
+    lens = [11, 19, 33, 64, 96, 128, 160, 192, 224, 251]
+    rng = random.Random(1)
+    strings = [bytes(rng.choice(lens)) for _ in range(300)]
+    assert_batch_matches_oracle(L, O, fprod, forc, strings)
+    try:
+        L.configure(exhaustive=1)
+        res = assert_batch_matches_oracle(L, O, fprod, forc, strings[:40])
+        for i, s in enumerate(strings[:40]):
+            n = len(s)
+            assert res.n_tuples[i] == 2 * n * n + 3 * n + 1
+    finally:
+        L.configure()
+
+
+def test_epsilon_dense_medium(L, O, gpu):
+    img = gen_image(O, 1, 4096, 12)
+    forc, fprod = O.Frozen.from_bytes(img), L.Fst.from_image(img)
+    assert_batch_matches_oracle(L, O, fprod, forc, [bytes(33), bytes(19), bytes(11), bytes(64)])
+
+
+def test_high_degree_states_use_search(L, O, gpu):
+    # states with > 32 arcs exercise the G-ary equal_range narrowing and multi-chunk expansions
+    rng = random.Random(77)
+    n = 6
+    arcs = []
+    for s in range(n):
+        for _ in range(rng.randint(60, 300)):
+            il = 0 if rng.random() < 0.1 else rng.randint(1, 40)
+            arcs.append((s, il, rng.randint(0, 5), float(rng.randint(0, 2)), rng.randrange(n)))
+    spec = Spec(n, 0, [0.0 if rng.random() < 0.5 else None for _ in range(n)], arcs)
+    fprod, forc, _ = frozen_pair(L, O, spec)
+    strings = [bytes(rng.randint(0, 39) for _ in range(rng.randint(0, 5))) for _ in range(60)]
+    for lanes in (0, 4, 32):
+        L.configure(lanes_per_string=lanes)
+        try:
+            assert_batch_matches_oracle(L, O, fprod, forc, strings)
+        finally:
+            L.configure()
+
+
+def test_cycle_hazard_is_reported(L, O, gpu):
+    from test_oracle_golden import CYCLE_CASE
+    n, finals, arcs, s = CYCLE_CASE
+    fprod, forc, _ = frozen_pair(L, O, Spec(n, 0, finals, arcs))
+    data, offsets = L.pack_strings([s, b""])
+    res = L.compose_frozen_shortest_path_batch(fprod, data, offsets)
+    assert res.status[0] == L.CYCLE
+    assert L.compose_frozen_shortest_path(L.MutableFst.compile_string(s), fprod, 1) is None   # reference: OOM -> invalid handle
