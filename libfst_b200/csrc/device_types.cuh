@@ -71,7 +71,8 @@ struct SearchParams {
   uint64_t arena_stride;
   uint32_t hash_cap;       // power of two
   uint32_t tuple_cap;
-  uint32_t heap_cap;
+  uint32_t heap_cap;       // binary-heap entries (serial path) / 128-byte chunks (warp path)
+  uint32_t bag_cap;        // warp path: unsorted future ids
   uint32_t exhaustive;
   // work queue + counters
   uint32_t* queue_head;

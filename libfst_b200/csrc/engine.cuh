@@ -14,7 +14,7 @@
 #include <vector>
 
 #include "csp_kernels.cuh"
-#include "csp_fast.cuh"
+#include "csp_warp.cuh"
 #include "host_fst.hpp"
 
 namespace fstb200 {
@@ -185,15 +185,16 @@ class Engine {
     const uint32_t* d_order = nullptr;
     for (uint32_t pass = 0;; pass++) {
       bc->passes++;
-      uint32_t hash_cap, heap_cap; uint64_t stride;
+      uint32_t hash_cap, heap_cap, bag_cap, smem_per_warp; uint64_t stride;
       const bool fast = !fst->serial;
       if (fast && tuple_cap > kMaxFastTuples) {
         mark_too_large_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_status, d_path_len_, n);
         bc->launches++;
         break;
       }
-      layout_for(fast, tuple_cap, hash_cap, heap_cap, stride);
-      uint32_t max_groups = max_resident_groups(G, fst->serial);
+      layout_for(fast, tuple_cap, hash_cap, heap_cap, bag_cap, stride, smem_per_warp);
+      if (fast) G = 32;
+      uint32_t max_groups = max_resident_groups(G, fst->serial, smem_per_warp);
       uint32_t want = std::min<uint32_t>(n_items, max_groups);
       uint64_t ws = workspace_budget(cfg);
       uint32_t fit = (uint32_t)std::min<uint64_t>(ws / stride, 0xFFFFFFFFull);
@@ -210,21 +211,21 @@ class Engine {
       } else {
         blocks = 1; gpb = std::min(want, fit); threads = gpb * G;
       }
-      FSTB_CUDA(ensure_workspace((uint64_t)blocks * gpb * stride, fast, hash_cap, tuple_cap, heap_cap, stride, blocks * gpb, stream));
+      FSTB_CUDA(ensure_workspace((uint64_t)blocks * gpb * stride, fast, hash_cap, tuple_cap, heap_cap, bag_cap, stride, blocks * gpb, stream));
       bc->launches += init_launches_; init_launches_ = 0;
 
       SearchParams p{};
       p.fst = fst->view;
       p.bytes = d_bytes; p.offsets = d_offsets; p.order = d_order; p.n_items = n_items;
       p.arena = static_cast<uint8_t*>(d_workspace_); p.arena_stride = stride;
-      p.hash_cap = hash_cap; p.tuple_cap = tuple_cap; p.heap_cap = heap_cap; p.exhaustive = cfg.exhaustive;
+      p.hash_cap = hash_cap; p.tuple_cap = tuple_cap; p.heap_cap = heap_cap; p.bag_cap = bag_cap; p.exhaustive = cfg.exhaustive;
       p.queue_head = d_cnt + 0;
       p.pool_cursor = reinterpret_cast<unsigned long long*>(d_cnt + 2);
       p.relax_counter = reinterpret_cast<unsigned long long*>(d_cnt + 4);
       p.tuple_counter = reinterpret_cast<unsigned long long*>(d_cnt + 6);
       p.status = d_status; p.path_len = d_path_len_; p.pool_off = d_pool_off_; p.final_w = d_final; p.n_tuples = d_ntuples;
       p.pool = d_pool_; p.pool_cap = pool_cap_;
-      launch_search(G, fst->serial, blocks, threads, p, stream);
+      launch_search(G, fst->serial, blocks, threads, smem_per_warp, p, stream);
       bc->launches++;
       FSTB_CUDA(cudaGetLastError());
       // any string that overflowed its arena (or the pool)?
@@ -326,12 +327,12 @@ class Engine {
     FSTB_CUDA(cudaEventRecord(ev0_, stream));
     for (;;) {
       bc->passes++;
-      uint32_t hash_cap, heap_cap; uint64_t stride;
+      uint32_t hash_cap, heap_cap, bag_cap, smem_per_warp; uint64_t stride;
       const bool fast = !serial;
       if (fast && tuple_cap > kMaxFastTuples) { *status = kStTooLarge; return cudaSuccess; }
-      layout_for(fast, tuple_cap, hash_cap, heap_cap, stride);
+      layout_for(fast, tuple_cap, hash_cap, heap_cap, bag_cap, stride, smem_per_warp);
       if (stride > workspace_budget(cfg)) { *status = kStTooLarge; return cudaSuccess; }
-      FSTB_CUDA(ensure_workspace(stride, fast, hash_cap, tuple_cap, heap_cap, stride, 1, stream));
+      FSTB_CUDA(ensure_workspace(stride, fast, hash_cap, tuple_cap, heap_cap, bag_cap, stride, 1, stream));
       bc->launches += init_launches_; init_launches_ = 0;
       FSTB_CUDA(cudaMemsetAsync(d_cnt, 0, 64, stream));
       SearchParams p{};
@@ -345,15 +346,19 @@ class Engine {
       p.lhs.weight = reinterpret_cast<const double*>(d_lhs + o_w);
       p.lhs.next = reinterpret_cast<const uint32_t*>(d_lhs + o_nx);
       p.arena = static_cast<uint8_t*>(d_workspace_); p.arena_stride = stride;
-      p.hash_cap = hash_cap; p.tuple_cap = tuple_cap; p.heap_cap = heap_cap; p.exhaustive = cfg.exhaustive;
+      p.hash_cap = hash_cap; p.tuple_cap = tuple_cap; p.heap_cap = heap_cap; p.bag_cap = bag_cap; p.exhaustive = cfg.exhaustive;
       p.queue_head = d_cnt + 0;
       p.pool_cursor = reinterpret_cast<unsigned long long*>(d_cnt + 2);
       p.relax_counter = reinterpret_cast<unsigned long long*>(d_cnt + 4);
       p.tuple_counter = reinterpret_cast<unsigned long long*>(d_cnt + 6);
       p.status = d_status1_; p.path_len = d_path_len_; p.pool_off = d_pool_off_; p.final_w = d_final1_; p.n_tuples = d_out_len_;
       p.pool = d_pool_; p.pool_cap = pool_cap_;
-      if (serial) csp_general_kernel<true><<<1, 32, 0, stream>>>(p);
-      else csp_general_fast_kernel<<<1, 32, 0, stream>>>(p);
+      if (serial) {
+        csp_general_kernel<true><<<1, 32, 0, stream>>>(p);
+      } else {
+        if (smem_per_warp > 40 * 1024) cudaFuncSetAttribute(csp_general_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_per_warp);
+        csp_general_warp_kernel<<<1, 32, smem_per_warp, stream>>>(p);
+      }
       bc->launches++;
       FSTB_CUDA(cudaGetLastError());
       struct { int32_t st; uint32_t plen; double fw; } r;
@@ -410,18 +415,24 @@ class Engine {
   bool layout_fast_ = false; uint32_t layout_heap_cap_ = 0;
 
   // arena geometry for a per-string tuple capacity
-  static void layout_for(bool fast, uint32_t& tuple_cap, uint32_t& hash_cap, uint32_t& heap_cap, uint64_t& stride) {
+  static void layout_for(bool fast, uint32_t& tuple_cap, uint32_t& hash_cap, uint32_t& heap_cap, uint32_t& bag_cap, uint64_t& stride,
+                         uint32_t& smem_per_warp) {
     if (fast) {
       if (tuple_cap < 256) tuple_cap = 256;
       hash_cap = (uint32_t)std::min<uint64_t>(0xFFFFFFF0ull, (uint64_t)tuple_cap * 100 / 65 + 16);
-      heap_cap = 96 + tuple_cap / 12;     // 128-byte chunks of 31 ids: ~2.6 queued ids per tuple
-      stride = fast_layout(hash_cap, tuple_cap, heap_cap).total;
+      heap_cap = 96 + tuple_cap / 24;     // 128-byte chunks of 31 ids: ~1.3 queued ids per tuple
+      bag_cap = tuple_cap;                // also the back-track scratch (path <= tuples)
+      WarpLayout L = warp_layout(hash_cap, tuple_cap, heap_cap, bag_cap);
+      stride = L.total;
+      smem_per_warp = L.smem_words * 4;
     } else {
       hash_cap = 1024;
       while ((uint64_t)hash_cap * 6 / 10 < tuple_cap && hash_cap < (1u << 31)) hash_cap <<= 1;
       tuple_cap = (uint32_t)((uint64_t)hash_cap * 6 / 10);
       heap_cap = tuple_cap * 3;
+      bag_cap = 0;
       stride = arena_bytes(hash_cap, tuple_cap, heap_cap);
+      smem_per_warp = 0;
     }
   }
 
@@ -434,28 +445,25 @@ class Engine {
     return 8;
   }
 
-  uint32_t max_resident_groups(uint32_t G, bool serial) {
+  uint32_t max_resident_groups(uint32_t G, bool serial, uint32_t smem_per_warp) {
     int bps = 0;
-    const void* fn = kernel_ptr(G, serial);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, 128, serial ? 0 : (128 / G) * 64 * sizeof(uint2)) != cudaSuccess || bps <= 0) bps = 4;
+    const void* fn = serial ? kernel_ptr(G) : (const void*)csp_batch_warp_kernel;
+    const size_t sm = serial ? 0 : (size_t)smem_per_warp * 4;
+    if (!serial && sm > 40 * 1024) cudaFuncSetAttribute(csp_batch_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, 128, sm) != cudaSuccess || bps <= 0) bps = 1;
     return (uint32_t)bps * (uint32_t)sm_count * (128 / G);
   }
-  static const void* kernel_ptr(uint32_t G, bool serial) {
-    if (serial) {
-      switch (G) { case 32: return (const void*)csp_batch_kernel<32, true>; case 16: return (const void*)csp_batch_kernel<16, true>;
-                   case 8: return (const void*)csp_batch_kernel<8, true>; default: return (const void*)csp_batch_kernel<4, true>; }
-    }
-    switch (G) { case 32: return (const void*)csp_batch_fast_kernel<32>; case 16: return (const void*)csp_batch_fast_kernel<16>;
-                 case 8: return (const void*)csp_batch_fast_kernel<8>; default: return (const void*)csp_batch_fast_kernel<4>; }
+  static const void* kernel_ptr(uint32_t G) {
+    switch (G) { case 32: return (const void*)csp_batch_kernel<32, true>; case 16: return (const void*)csp_batch_kernel<16, true>;
+                 case 8: return (const void*)csp_batch_kernel<8, true>; default: return (const void*)csp_batch_kernel<4, true>; }
   }
-  static void launch_search(uint32_t G, bool serial, uint32_t blocks, uint32_t threads, const SearchParams& p, cudaStream_t s) {
+  static void launch_search(uint32_t G, bool serial, uint32_t blocks, uint32_t threads, uint32_t smem_per_warp, const SearchParams& p,
+                            cudaStream_t s) {
     if (serial) {
       switch (G) { case 32: csp_batch_kernel<32, true><<<blocks, threads, 0, s>>>(p); break; case 16: csp_batch_kernel<16, true><<<blocks, threads, 0, s>>>(p); break;
                    case 8: csp_batch_kernel<8, true><<<blocks, threads, 0, s>>>(p); break; default: csp_batch_kernel<4, true><<<blocks, threads, 0, s>>>(p); break; }
     } else {
-      const size_t sm = (size_t)(threads / G) * 64 * sizeof(uint2);
-      switch (G) { case 32: csp_batch_fast_kernel<32><<<blocks, threads, sm, s>>>(p); break; case 16: csp_batch_fast_kernel<16><<<blocks, threads, sm, s>>>(p); break;
-                   case 8: csp_batch_fast_kernel<8><<<blocks, threads, sm, s>>>(p); break; default: csp_batch_fast_kernel<4><<<blocks, threads, sm, s>>>(p); break; }
+      csp_batch_warp_kernel<<<blocks, threads, (size_t)(threads / 32) * smem_per_warp, s>>>(p);
     }
   }
 
@@ -469,8 +477,8 @@ class Engine {
   }
   uint64_t budget_cache_ = 0;
 
-  cudaError_t ensure_workspace(uint64_t bytes, bool fast, uint32_t hash_cap, uint32_t tuple_cap, uint32_t heap_cap, uint64_t stride,
-                               uint32_t groups, cudaStream_t s) {
+  cudaError_t ensure_workspace(uint64_t bytes, bool fast, uint32_t hash_cap, uint32_t tuple_cap, uint32_t heap_cap, uint32_t bag_cap,
+                               uint64_t stride, uint32_t groups, cudaStream_t s) {
     if (bytes > workspace_bytes_) {
       if (d_workspace_) { FSTB_CUDA(cudaStreamSynchronize(s)); FSTB_CUDA(cudaFree(d_workspace_)); d_workspace_ = nullptr; workspace_bytes_ = 0; }
       FSTB_CUDA(cudaMalloc(&d_workspace_, bytes));
@@ -484,7 +492,7 @@ class Engine {
       if (fast) {
         uint64_t words = ((uint64_t)hash_cap * 4 + tuple_cap / 60 + 64) * groups;
         uint32_t blocks = (uint32_t)std::min<uint64_t>((words + 255) / 256, (uint64_t)sm_count * 32);
-        fast_arena_init_kernel<<<blocks, 256, 0, s>>>(static_cast<uint8_t*>(d_workspace_), stride, groups, hash_cap, tuple_cap, heap_cap);
+        warp_arena_init_kernel<<<blocks, 256, 0, s>>>(static_cast<uint8_t*>(d_workspace_), stride, groups, hash_cap, tuple_cap, heap_cap, bag_cap);
         init_launches_++;
         FSTB_CUDA(cudaGetLastError());
       } else {
