@@ -115,7 +115,8 @@ typedef enum {
   FST_B200_CYCLE = 2,       /* reference hazard: back-pointer cycle through zero-weight
                                epsilon loops (the reference runs out of memory here and
                                returns FST_INVALID_HANDLE); reported, never emitted      */
-  FST_B200_TOO_LARGE = 3    /* search state does not fit the configured device budget    */
+  FST_B200_TOO_LARGE = 3,   /* search state does not fit the configured device budget    */
+  FST_B200_INTERNAL = 4     /* engine self-check failed (never expected; report a bug)   */
 } FstB200Status;
 
 /* Result of one batched call; all arrays are owned by the library and live in
@@ -186,6 +187,9 @@ typedef struct {
   uint32_t exhaustive;        /* 1 = never stop before the queue is empty (reference's
                                  literal behaviour); 0 = stop once no remaining tuple can
                                  change the result (identical output, proven in DESIGN.md) */
+  uint32_t engine;            /* kernel choice for byte-string batches: 0 = auto, 1 = general
+                                 warp kernel, 2 = lean kernel + hash table, 3 = lean kernel +
+                                 dense (position x state) table; all produce identical output */
 } FstB200Config;
 FstError fst_b200_configure(const FstB200Config* cfg);
 /* Counters of the last batched call on this thread: kernels launched, relaxations. */

@@ -20,7 +20,7 @@ FST_OK, FST_OOM, FST_INVALID_ARG, FST_INVALID_STATE, FST_IO_ERROR = 0, 1, 2, 3, 
 FST_NO_STATE = 0xFFFFFFFF
 FST_EPSILON = 0
 FST_INVALID_HANDLE = 0xFFFFFFFFFFFFFFFF
-PATH, NO_PATH, CYCLE, TOO_LARGE = 0, 1, 2, 3
+PATH, NO_PATH, CYCLE, TOO_LARGE, INTERNAL = 0, 1, 2, 3, 4
 
 
 class FstArc(C.Structure):
@@ -44,7 +44,7 @@ class DeviceOut(C.Structure):
 
 class Config(C.Structure):
     _fields_ = [("workspace_bytes", C.c_uint64), ("lanes_per_string", C.c_uint32), ("tuples_hint", C.c_uint32),
-                ("exhaustive", C.c_uint32)]
+                ("exhaustive", C.c_uint32), ("engine", C.c_uint32)]
 
 
 EXPORTS = {
@@ -122,8 +122,11 @@ def device_count() -> int:
     return lib().fst_b200_device_count()
 
 
-def configure(workspace_bytes=0, lanes_per_string=0, tuples_hint=0, exhaustive=0):
-    cfg = Config(workspace_bytes, lanes_per_string, tuples_hint, exhaustive)
+ENGINE_AUTO, ENGINE_WARP, ENGINE_LEAN_HASH, ENGINE_LEAN_DENSE = 0, 1, 2, 3
+
+
+def configure(workspace_bytes=0, lanes_per_string=0, tuples_hint=0, exhaustive=0, engine=0):
+    cfg = Config(workspace_bytes, lanes_per_string, tuples_hint, exhaustive, engine)
     rc = lib().fst_b200_configure(C.byref(cfg))
     if rc != FST_OK:
         raise ValueError(f"fst_b200_configure failed: {rc}")

@@ -430,7 +430,8 @@ struct BatchResultImpl {
 };
 
 static int32_t map_status(int32_t s) {
-  switch (s) { case kStPath: return FST_B200_PATH; case kStNoPath: return FST_B200_NO_PATH; case kStCycle: return FST_B200_CYCLE; default: return FST_B200_TOO_LARGE; }
+  switch (s) { case kStPath: return FST_B200_PATH; case kStNoPath: return FST_B200_NO_PATH; case kStCycle: return FST_B200_CYCLE;
+               case kStInternal: return FST_B200_INTERNAL; default: return FST_B200_TOO_LARGE; }
 }
 
 FstError fst_compose_frozen_shortest_path_batch(FstHandle b, const uint8_t* bytes, const uint64_t* offsets,
@@ -485,7 +486,7 @@ FstError fst_compose_frozen_shortest_path_batch(FstHandle b, const uint8_t* byte
     if (!ok) { cudaGetLastError(); free_dev(); return FST_OOM; }
     if (nbytes) cudaMemcpyAsync(d_bytes, bytes + offsets[0], nbytes, cudaMemcpyHostToDevice, stream);
     cudaMemcpyAsync(d_offsets, rel.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, stream);
-    err = en->run_batch(img, d_bytes, d_offsets, n, d_status, d_poff, d_il, d_ol, d_w, d_fin, d_nt, path_cap, d_ooff, d_obytes, path_cap, stream, &bc);
+    err = en->run_batch(img, d_bytes, d_offsets, n, (uint32_t)max_len, d_status, d_poff, d_il, d_ol, d_w, d_fin, d_nt, path_cap, d_ooff, d_obytes, path_cap, stream, &bc);
     if (err != cudaSuccess) { free_dev(); return err == cudaErrorMemoryAllocation ? FST_OOM : FST_INVALID_STATE; }
     if (bc.path_required > path_cap && attempt < 4) { path_cap = bc.path_required * 2; free_dev(); continue; }
     break;
@@ -563,7 +564,7 @@ FstError fst_b200_batch_device(FstHandle b, const uint8_t* d_bytes, const uint64
   if (!img) return err == cudaErrorMemoryAllocation ? FST_OOM : FST_INVALID_STATE;
   std::lock_guard<std::mutex> lk(en->mu);
   BatchCounters bc;
-  err = en->run_batch(img, d_bytes, d_offsets, n_strings, o->d_status, o->d_path_offsets, o->d_ilabels, o->d_olabels, o->d_weights,
+  err = en->run_batch(img, d_bytes, d_offsets, n_strings, max_len, o->d_status, o->d_path_offsets, o->d_ilabels, o->d_olabels, o->d_weights,
                       o->d_final_weights, o->d_n_tuples, o->path_capacity, nullptr, nullptr, 0, static_cast<cudaStream_t>(stream), &bc);
   t_last = bc;
   if (err != cudaSuccess) return err == cudaErrorMemoryAllocation ? FST_OOM : FST_INVALID_STATE;
@@ -576,7 +577,8 @@ FstError fst_b200_configure(const FstB200Config* cfg) {
   uint32_t g = cfg->lanes_per_string;
   if (!(g == 0 || g == 4 || g == 8 || g == 16 || g == 32)) return FST_INVALID_ARG;
   Config& c = global_config();
-  c.workspace_bytes = cfg->workspace_bytes; c.lanes_per_string = g; c.tuples_hint = cfg->tuples_hint; c.exhaustive = cfg->exhaustive;
+  if (cfg->engine > 3) return FST_INVALID_ARG;
+  c.workspace_bytes = cfg->workspace_bytes; c.lanes_per_string = g; c.tuples_hint = cfg->tuples_hint; c.exhaustive = cfg->exhaustive; c.engine = cfg->engine;
   return FST_OK;
 }
 

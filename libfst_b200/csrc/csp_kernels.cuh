@@ -61,6 +61,7 @@ struct Group {
   __device__ __forceinline__ unsigned match_any(unsigned long long v) const {
     return (__match_any_sync(mask, v) >> base) & kBits;
   }
+  __device__ __forceinline__ unsigned match_any32(unsigned v) const { return (__match_any_sync(mask, v) >> base) & kBits; }
   __device__ __forceinline__ unsigned lt_mask() const { return (1u << lane) - 1u; }
 };
 

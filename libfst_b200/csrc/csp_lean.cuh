@@ -1,0 +1,704 @@
+// Lean exact search for the BATCHED path: byte-string left operands (linear,
+// epsilon-free, unit weights) against a frozen transducer whose arc weights are
+// finite and non-negative.  One G-lane group (G = 32 or 16) per string.
+//
+// Same observable behaviour as csp_warp.cuh (the reference's pop order, ids in
+// first-touch order, its relax/tie rule and final pick; compose-shortest-path.zig
+// :55-61, :70-89, :91-144, :159-179) — what changes is the cost per pop:
+//
+//   * TABLE.  Either a DENSE direct-indexed table  e = ((p * S + s) * 2 + filter)
+//     of 16-byte records {dist, id, prev} (no hashing, no probing, neighbouring
+//     transducer states share DRAM sectors) when (len+1) * S * 2 records fit the
+//     per-string budget, or the open-addressing HASH table of 32-byte slots.
+//   * BACK-POINTER = predecessor id only.  The reference stores (prev, ilabel,
+//     olabel, weight) (:44-49); for a linear left operand the arc is a function
+//     of (prev tuple, tuple, dist[prev], dist[tuple]): it is the FIRST arc in
+//     expansion order from prev's transducer state to the tuple's state, of the
+//     tuple's kind (match / input-epsilon), whose relaxation reaches dist[tuple]
+//     — later arcs of the same expansion never replace it (they would need a
+//     strictly smaller distance, or on a tie smaller (ilabel, olabel), impossible
+//     in frozen arc order).  The back-track recomputes it for the P path arcs
+//     instead of storing it for all N tuples.
+//   * FOLD WITHOUT LOOPS.  Candidates of one expansion that hit the same target
+//     are grouped with MATCH.ANY; the minimum new distance of each group is two
+//     REDUX.MIN over the peers (distances are >= +0.0, so the IEEE bit pattern
+//     orders like the value); the first lane of the group applies the take rule
+//     once.  Equivalent to relaxing the candidates one by one in arc order
+//     (DESIGN.md §exactness-fold).
+//   * READY SET.  Bitmap over discovery ids, 32 ids per word, in HBM; the line
+//     (G words = 32*G ids) that holds the current minimum lives in shared memory
+//     (the WINDOW) and a one-bit-per-line summary sits above it.  The reference's
+//     pop order sweeps ids almost monotonically (measured: 99.5 % of pops stay in
+//     the same 1024-id line on the headline workload), so a pop is one LDS +
+//     ballot, and an insert is one shared or global atomic OR — no loops.
+//   * FUTURE SET (tuples whose tentative distance is above the current level):
+//     unchanged from csp_warp.cuh — unsorted bag, turned into a radix heap over
+//     the IEEE bit pattern only when a second level is really needed.
+#pragma once
+#include "csp_kernels.cuh"
+#include "csp_warp.cuh"   // kChunkIds, kNoChunk, kMaxFastTuples, bucket_of
+
+namespace fstb200 {
+
+// 16-byte record of the dense table; all-ones bytes = never touched (id == kNone).
+struct __align__(16) DenseEnt { double dist; uint32_t id; uint32_t prev; };
+static_assert(sizeof(DenseEnt) == 16, "DenseEnt");
+// 32-byte slot of the hash table (one DRAM sector); key all-ones = empty.  The record half is 16-byte aligned.
+struct __align__(32) LeanSlot { unsigned long long key; unsigned long long spare; double dist; uint32_t id; uint32_t prev; };
+static_assert(sizeof(LeanSlot) == 32, "LeanSlot");
+
+struct LeanLayout {
+  uint64_t off_tab, off_keyof, off_l0, off_bag, off_chunks, total;
+  uint64_t tab_bytes, l0_bytes;
+  uint32_t n1;           // summary words (one bit per window line)
+  uint32_t smem_words;   // u32 words of shared memory per group
+};
+// `tab_entries`: dense = (max_len + 1) * S * 2 records of 16 B; hash = slots of 32 B.
+__host__ __device__ inline LeanLayout lean_layout(int G, bool dense, uint64_t tab_entries, uint32_t tuple_cap, uint32_t chunk_cap,
+                                                  uint32_t bag_cap) {
+  LeanLayout L;
+  auto al = [](uint64_t x) { return (x + 127) & ~127ull; };
+  const uint32_t ids_per_line = 32u * (uint32_t)G;
+  const uint32_t lines = (tuple_cap + ids_per_line - 1) / ids_per_line;
+  L.n1 = (lines + 31) / 32;
+  L.tab_bytes = al(tab_entries * (dense ? 16ull : 32ull));
+  L.l0_bytes = al((uint64_t)lines * G * 4);
+  L.off_tab = 0;
+  L.off_keyof = L.tab_bytes;
+  L.off_l0 = L.off_keyof + al((uint64_t)tuple_cap * 8);
+  L.off_bag = L.off_l0 + L.l0_bytes;
+  L.off_chunks = L.off_bag + al((uint64_t)bag_cap * 4);
+  L.total = (L.off_chunks + (uint64_t)chunk_cap * 128 + 255) & ~255ull;
+  L.smem_words = (128 + (uint32_t)G + L.n1 + 3) & ~3u;   // radix buckets (64 x uint2) + window + summary
+  return L;
+}
+
+struct LeanArena {
+  uint8_t* tab;                 // DenseEnt[] or LeanSlot[]
+  unsigned long long* key_of;   // id -> packed tuple key
+  uint32_t* l0;                 // ready bitmap, 32 ids per word (HBM)
+  uint32_t* bag;                // unsorted future ids; back-track scratch afterwards
+  uint32_t* chunks;             // radix-heap chunk pool
+  uint2* bucket;                // smem [64]
+  uint32_t* win;                // smem [G]   the window: line `wline` of l0
+  uint32_t* l1;                 // smem [n1]  bit per line: line has bits in HBM
+  uint64_t tab_entries;
+  uint32_t S;                   // transducer states (dense index stride)
+  uint32_t tuple_cap, chunk_cap, bag_cap, n1;
+};
+
+// Arena initialisation (layout change): table bytes 0xFF (dense: id == kNone; hash: key == empty), bitmap zero.
+__global__ void lean_arena_init_kernel(uint8_t* arena, uint64_t stride, uint32_t n_arenas, uint64_t off_l0, uint64_t tab_bytes,
+                                       uint64_t l0_bytes) {
+  const uint64_t tw = tab_bytes / 16, bw = l0_bytes / 16, per = tw + bw, total = per * n_arenas;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t ar = i / per, w = i % per;
+    uint8_t* base = arena + ar * stride;
+    if (w < tw) reinterpret_cast<uint4*>(base)[w] = make_uint4(~0u, ~0u, ~0u, ~0u);
+    else reinterpret_cast<uint4*>(base + off_l0)[w - tw] = make_uint4(0, 0, 0, 0);
+  }
+}
+
+struct LeanState {
+  uint32_t n_tuples;
+  uint32_t chunk_next, free_head, bag_len;
+  uint32_t wline;                // line held in the window, kNone = none
+  unsigned long long occupied;   // radix buckets in use
+  unsigned long long last;       // bit pattern of the current level distance
+  unsigned long long relax_calls;
+  bool low_pending;              // a ready id below the window was inserted
+  bool overflow, sorted, lossy;
+};
+
+template <int G> struct LgG { static constexpr int v = G == 32 ? 5 : (G == 16 ? 4 : (G == 8 ? 3 : 2)); };
+
+__device__ __forceinline__ uint32_t ldcg_u32(const uint32_t* p) { return __ldcg(p); }
+
+// ── table access ──
+template <bool DENSE>
+__device__ __forceinline__ uint32_t lean_dense_index(const LeanArena& a, unsigned long long K) {
+  return (((uint32_t)(K >> 34)) * a.S + (uint32_t)(K >> 2)) * 2u + (uint32_t)(K & 1u);
+}
+// Find the record of key K: position and contents; id == kNone <=> not present (hash: `pos` is then the
+// empty slot that ended the probe — pass it to lean_claim before storing).
+template <bool DENSE>
+__device__ __forceinline__ void lean_lookup(const LeanArena& a, unsigned long long K, uint32_t& pos, double& dist, uint32_t& id,
+                                            uint32_t& prev) {
+  if (DENSE) {
+    pos = lean_dense_index<true>(a, K);
+    const uint4 v = *reinterpret_cast<const uint4*>(a.tab + (uint64_t)pos * 16);
+    dist = __hiloint2double((int)v.y, (int)v.x); id = v.z; prev = v.w;
+  } else {
+    const LeanSlot* tab = reinterpret_cast<const LeanSlot*>(a.tab);
+    const uint32_t cap = (uint32_t)a.tab_entries;
+    uint32_t i = (uint32_t)(((unsigned long long)hash_key(K) * cap) >> 32);
+    for (;;) {
+      const unsigned long long k = tab[i].key;
+      if (k == kEmptyKey) { pos = i; dist = d_inf(); id = kNone; prev = kNone; return; }
+      if (k == K) {
+        pos = i;
+        const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(&tab[i]) + 16);
+        dist = __hiloint2double((int)v.y, (int)v.x); id = v.z; prev = v.w;
+        return;
+      }
+      if (++i == cap) i = 0;
+    }
+  }
+}
+// Hash table: claim a slot for the new key K, starting at the empty position the probe found (other
+// leaders of the group insert other keys concurrently).  Dense table: nothing to do.
+template <bool DENSE>
+__device__ __forceinline__ uint32_t lean_claim(const LeanArena& a, unsigned long long K, uint32_t pos) {
+  if (DENSE) return pos;
+  LeanSlot* tab = reinterpret_cast<LeanSlot*>(a.tab);
+  const uint32_t cap = (uint32_t)a.tab_entries;
+  for (;;) {
+    if (atomicCAS(&tab[pos].key, kEmptyKey, K) == kEmptyKey) return pos;
+    if (++pos == cap) pos = 0;
+  }
+}
+// Write a record.  The hash variant rewrites the key half too: plain stores keep this SM's L1 copy of the
+// sector consistent with what later plain-load probes must see (the claiming CAS acts on L2 only).
+template <bool DENSE>
+__device__ __forceinline__ void lean_store(const LeanArena& a, uint32_t pos, unsigned long long K, double dist, uint32_t id, uint32_t prev) {
+  const uint4 v = make_uint4((uint32_t)__double2loint(dist), (uint32_t)__double2hiint(dist), id, prev);
+  if (DENSE) {
+    *reinterpret_cast<uint4*>(a.tab + (uint64_t)pos * 16) = v;
+  } else {
+    uint4* sl = reinterpret_cast<uint4*>(a.tab + (uint64_t)pos * 32);
+    sl[0] = make_uint4((uint32_t)K, (uint32_t)(K >> 32), 0u, 0u);
+    sl[1] = v;
+  }
+}
+template <bool DENSE>
+__device__ __forceinline__ double lean_dist_of_id(const LeanArena& a, uint32_t id) {
+  uint32_t pos, i2, pr; double d;
+  lean_lookup<DENSE>(a, a.key_of[id], pos, d, i2, pr);
+  return d;
+}
+
+// ── ready set ──
+// Insert ids (collective over the group; one atomic OR per inserting lane).
+template <int G>
+__device__ __forceinline__ void lean_ready_insert(const Group<G>& g, const LeanArena& a, LeanState& st, bool active, uint32_t id) {
+  bool low = false;
+  if (active) {
+    const uint32_t line = id >> (5 + LgG<G>::v);
+    const uint32_t bit = 1u << (id & 31u);
+    if (line == st.wline) {
+      atomicOr(&a.win[(id >> 5) & (G - 1)], bit);
+    } else {
+      atomicOr(&a.l0[id >> 5], bit);
+      atomicOr(&a.l1[line >> 5], 1u << (line & 31u));
+      low = st.wline != kNone && line < st.wline;
+    }
+  }
+  if (g.any(low)) st.low_pending = true;
+  g.sync();
+}
+// Write the window back (it holds ids above a newly inserted smaller one).
+template <int G>
+__device__ __forceinline__ void lean_window_evict(const Group<G>& g, const LeanArena& a, LeanState& st) {
+  if (st.wline != kNone) {
+    const uint32_t w = a.win[g.lane];
+    if (w) __stcg(&a.l0[st.wline * G + g.lane], w);
+    if (g.any(w != 0)) { if (g.lane == 0) a.l1[st.wline >> 5] |= 1u << (st.wline & 31u); }
+    a.win[g.lane] = 0;
+    st.wline = kNone;
+  }
+  g.sync();
+}
+// Load the lowest non-empty line into the window.  False: the ready set is empty.
+template <int G>
+__device__ __forceinline__ bool lean_window_next(const Group<G>& g, const LeanArena& a, LeanState& st) {
+  const uint32_t words = min(a.n1, (st.n_tuples >> (10 + LgG<G>::v)) + 1u);
+  for (uint32_t base = 0; base < words; base += G) {
+    const uint32_t i = base + g.lane;
+    const uint32_t v = i < words ? a.l1[i] : 0u;
+    const unsigned bal = g.ballot(v != 0);
+    if (bal) {
+      const int src = __ffs(bal) - 1;
+      const uint32_t vv = g.shfl(v, src);
+      const uint32_t line = ((base + src) << 5) + (__ffs(vv) - 1);
+      if ((int)g.lane == src) a.l1[i] = vv & (vv - 1);
+      st.wline = line;
+      uint32_t* wp = &a.l0[line * G + g.lane];
+      const uint32_t w = __ldcg(wp);
+      if (w) __stcg(wp, 0u);
+      a.win[g.lane] = w;
+      // the keys of this line are read one pop at a time: pull them into L1 now (32*G ids * 8 B)
+      const char* kp = reinterpret_cast<const char*>(a.key_of + (uint64_t)line * 32 * G) + (size_t)g.lane * 128;
+#pragma unroll
+      for (int r = 0; r < 2; r++) asm volatile("prefetch.global.L1 [%0];" ::"l"(kp + (size_t)r * G * 128));
+      g.sync();
+      return true;
+    }
+  }
+  st.wline = kNone;
+  return false;
+}
+
+// ── future set (radix heap; cold on single-level searches) ──
+template <int G>
+__device__ __forceinline__ uint32_t lean_chunk_alloc(const LeanArena& a, LeanState& st) {
+  uint32_t c;
+  if (st.free_head != kNoChunk) { c = st.free_head; st.free_head = a.chunks[(uint64_t)c * 32]; }
+  else if (st.chunk_next < a.chunk_cap) c = st.chunk_next++;
+  else { st.overflow = true; c = 0; }
+  return c;
+}
+template <int G>
+__device__ __forceinline__ void lean_bucket_push(const Group<G>& g, const LeanArena& a, LeanState& st, bool active, uint32_t id, uint32_t b) {
+  unsigned m = g.ballot(active);
+  const unsigned lt = g.lt_mask();
+  while (m) {
+    const int first = __ffs(m) - 1;
+    const uint32_t bb = g.shfl(b, first);
+    const bool mine = active && b == bb;
+    const unsigned same = g.ballot(mine);
+    m &= ~same;
+    const uint32_t k = __popc(same), rank = __popc(same & lt);
+    const bool empty = !((st.occupied >> (bb - 1)) & 1ull);
+    const uint2 hb = a.bucket[bb - 1];
+    uint32_t head = empty ? kNoChunk : hb.x, cnt = empty ? kChunkIds : hb.y;
+    const uint32_t space = kChunkIds - cnt;
+    if (mine && rank < space) a.chunks[(uint64_t)head * 32 + 1 + cnt + rank] = id;
+    uint32_t left = k > space ? k - space : 0, done = k - left;
+    if (left == 0) cnt += k;
+    while (left > 0) {
+      const uint32_t c = lean_chunk_alloc<G>(a, st);
+      if (st.overflow) return;
+      const uint32_t take = left < kChunkIds ? left : kChunkIds;
+      if (g.lane == 0) a.chunks[(uint64_t)c * 32] = head;
+      if (mine && rank >= done && rank < done + take) a.chunks[(uint64_t)c * 32 + 1 + (rank - done)] = id;
+      head = c; cnt = take; done += take; left -= take;
+    }
+    g.sync();
+    if (g.lane == 0) a.bucket[bb - 1] = make_uint2(head, cnt);
+    st.occupied |= 1ull << (bb - 1);
+    g.sync();
+  }
+}
+template <int G>
+__device__ __forceinline__ unsigned long long lean_group_min_u64(const Group<G>& g, unsigned long long v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(g.mask, v, o, G); v = t < v ? t : v; }
+  return v;
+}
+
+template <int G, bool DENSE>
+__device__ __forceinline__ void lean_build_radix(const Group<G>& g, const LeanArena& a, LeanState& st) {
+  st.sorted = true;
+  const uint32_t n = st.lossy ? st.n_tuples : st.bag_len;
+  for (uint32_t base = 0; base < n && !st.overflow; base += G) {
+    const uint32_t j = base + g.lane;
+    bool valid = false; uint32_t id = 0; unsigned long long k = 0;
+    if (j < n) {
+      id = st.lossy ? j : a.bag[j];
+      k = (unsigned long long)__double_as_longlong(lean_dist_of_id<DENSE>(a, id));
+      valid = k > st.last;
+    }
+    if (g.any(valid)) lean_bucket_push<G>(g, a, st, valid, id, valid ? bucket_of(k, st.last) : 1u);
+  }
+  st.bag_len = 0; st.lossy = false;
+}
+
+// Advance to the next distance level; false = the search is finished.
+template <int G, bool DENSE>
+__device__ __forceinline__ bool lean_advance_level(const SearchParams& p, const Group<G>& g, const LeanArena& a, LeanState& st,
+                                                bool have_best, double best_total, unsigned long long future_min) {
+  if (!st.sorted) {
+    const unsigned long long fm = lean_group_min_u64<G>(g, future_min);
+    if (fm == ~0ull) return false;
+    if (!p.exhaustive && have_best && __longlong_as_double((long long)fm) > best_total) return false;
+    lean_build_radix<G, DENSE>(g, a, st);
+    if (st.overflow) return false;
+  }
+  while (st.occupied) {
+    const uint32_t b0 = __ffsll((long long)st.occupied);   // bucket number 1..64
+    const uint2 hb = a.bucket[b0 - 1];
+    unsigned long long m = ~0ull;
+    {
+      uint32_t c = hb.x, cnt = hb.y;
+      while (c != kNoChunk) {
+        const uint32_t* ch = a.chunks + (uint64_t)c * 32;
+        const uint32_t next = ch[0];
+        for (uint32_t o = 0; o < cnt; o += G) {
+          if (o + g.lane < cnt) {
+            const uint32_t id = ch[1 + o + g.lane];
+            const unsigned long long k = (unsigned long long)__double_as_longlong(lean_dist_of_id<DENSE>(a, id));
+            if (k > st.last && bucket_of(k, st.last) == b0 && k < m) m = k;
+          }
+        }
+        c = next; cnt = kChunkIds;
+      }
+      m = lean_group_min_u64<G>(g, m);
+    }
+    st.occupied &= ~(1ull << (b0 - 1));
+    g.sync();
+    if (m == ~0ull) {   // only stale entries: recycle the chunks
+      uint32_t c = hb.x;
+      while (c != kNoChunk) {
+        const uint32_t next = a.chunks[(uint64_t)c * 32];
+        g.sync();
+        if (g.lane == 0) a.chunks[(uint64_t)c * 32] = st.free_head;
+        st.free_head = c;
+        g.sync();
+        c = next;
+      }
+      continue;
+    }
+    if (!p.exhaustive && have_best && __longlong_as_double((long long)m) > best_total) return false;
+    const unsigned long long old_last = st.last;
+    st.last = m;
+    uint32_t c = hb.x, cnt = hb.y;
+    while (c != kNoChunk && !st.overflow) {
+      const uint32_t* ch = a.chunks + (uint64_t)c * 32;
+      const uint32_t next = ch[0];
+      for (uint32_t o = 0; o < cnt && !st.overflow; o += G) {
+        bool valid = false; uint32_t id = 0; unsigned long long k = 0;
+        if (o + g.lane < cnt) {
+          id = ch[1 + o + g.lane];
+          k = (unsigned long long)__double_as_longlong(lean_dist_of_id<DENSE>(a, id));
+          valid = k > old_last && bucket_of(k, old_last) == b0;
+        }
+        lean_ready_insert<G>(g, a, st, valid && k == m, id);
+        const bool tb = valid && k != m;
+        if (g.any(tb)) lean_bucket_push<G>(g, a, st, tb, id, tb ? bucket_of(k, m) : 1u);
+      }
+      g.sync();
+      if (g.lane == 0) a.chunks[(uint64_t)c * 32] = st.free_head;   // recycle
+      st.free_head = c;
+      g.sync();
+      c = next; cnt = kChunkIds;
+    }
+    return !st.overflow;
+  }
+  return false;
+}
+
+// ── one relaxation candidate per lane ──
+// `first`: lanes that precede the other active lanes in the reference's expansion
+// order (match arcs :182-202 before input-epsilon arcs :254-278); only used to
+// number newly discovered tuples.
+template <int G, bool DENSE>
+__device__ __forceinline__ void lean_relax(const SearchParams& p, const Group<G>& g, const LeanArena& a, LeanState& st, uint32_t cur_id,
+                                           double cur_dist, bool active, unsigned long long K, double ew, unsigned first,
+                                           unsigned long long& future_min) {
+  const unsigned act = g.ballot(active);
+  if (act == 0) return;
+  st.relax_calls += __popc(act);
+  // group by target; the first lane of each group leads
+  unsigned peers;
+  if (DENSE) peers = g.match_any32(active ? lean_dense_index<true>(a, K) : (0xFFFFFF00u | g.lane));
+  else peers = g.match_any(active ? K : (0xFFFFFFFFFFFFFF00ull | g.lane));
+  const unsigned ldr = (unsigned)(__ffs(peers) - 1);
+  const bool leader = active && ldr == g.lane;
+  // minimum new distance over the group (bit pattern order == value order for x >= +0.0)
+  const double nd = cur_dist + ew;
+  const unsigned hi = (unsigned)__double2hiint(nd), lo = (unsigned)__double2loint(nd);
+  const unsigned pm = peers << g.base;
+  const unsigned mhi = __reduce_min_sync(pm, hi);
+  const unsigned mlo = __reduce_min_sync(pm, hi == mhi ? lo : 0xFFFFFFFFu);
+  const double ndmin = __hiloint2double((int)mhi, (int)mlo);
+  uint32_t pos = 0, old_id = 0, old_prev = kNone; double old_dist = d_inf();
+  if (leader) lean_lookup<DENSE>(a, K, pos, old_dist, old_id, old_prev);
+  const bool is_new = leader && old_id == kNone;
+  const unsigned newmask = g.ballot(is_new);
+  const uint32_t n_new = __popc(newmask);
+  if (st.n_tuples + n_new > a.tuple_cap) { st.overflow = true; return; }
+  bool lowered = false;
+  uint32_t my_id = old_id;
+  if (leader) {
+    if (is_new) {
+      const unsigned lt = g.lt_mask();
+      const bool in_first = (first >> g.lane) & 1u;
+      const uint32_t rank = in_first ? __popc(newmask & first & lt) : (__popc(newmask & first) + __popc(newmask & ~first & lt));
+      my_id = st.n_tuples + rank;   // discovery order == reference expansion order (:80-87)
+      a.key_of[my_id] = K;
+      pos = lean_claim<DENSE>(a, K, pos);
+    }
+    lowered = is_new || ndmin < old_dist;                                                         // :109-114, :137-142
+    const bool take = lowered || (ndmin == old_dist && (old_prev == kNone || cur_id < old_prev)); // :115-126
+    if (take) lean_store<DENSE>(a, pos, K, ndmin, my_id, cur_id);
+  }
+  st.n_tuples += n_new;
+  // queue: ready set if at the current level, else future set
+  const unsigned long long k = (unsigned long long)__double_as_longlong(ndmin);
+  const bool to_ready = lowered && k == st.last;
+  const bool to_future = lowered && k != st.last;
+  lean_ready_insert<G>(g, a, st, to_ready, my_id);
+  const unsigned f = g.ballot(to_future);
+  if (f) {
+    if (to_future && k < future_min) future_min = k;
+    if (st.sorted) {
+      lean_bucket_push<G>(g, a, st, to_future, my_id, to_future ? bucket_of(k, st.last) : 1u);
+    } else if (!st.lossy) {
+      const uint32_t cnt = __popc(f);
+      if (st.bag_len + cnt <= a.bag_cap) {
+        if (to_future) a.bag[st.bag_len + __popc(f & g.lt_mask())] = my_id;
+        st.bag_len += cnt;
+      } else {
+        st.lossy = true;   // bag abandoned; a rescan of all tuples rebuilds the future set if ever needed
+      }
+    }
+    g.sync();
+  }
+}
+
+// Recover the arc of the step prev -> tuple (see file header).  Returns false if none fits (internal error).
+__device__ inline bool lean_recover_arc(const DevFstView& F, const LhsBytes& lhs, unsigned long long Ku, unsigned long long Kv, double du,
+                                        double dv, PoolArc& out) {
+  const uint32_t pu = (uint32_t)(Ku >> 34), su = (uint32_t)(Ku >> 2), pv = (uint32_t)(Kv >> 34), sv = (uint32_t)(Kv >> 2);
+  const uint4 rec = __ldg(&F.state_rec[su]);
+  uint32_t lo, hi, il = 0;
+  const bool match = pv == pu + 1;
+  if (match) {
+    il = (uint32_t)__ldg(lhs.s + pu) + 1u;
+    uint32_t l = rec.y, h = rec.z;   // labels >= 1 start after the epsilon prefix
+    while (l < h) { const uint32_t m = l + (h - l) / 2; if (__ldg(F.ilabel + m) < il) l = m + 1; else h = m; }
+    lo = l; hi = rec.z;
+  } else {
+    lo = rec.x; hi = rec.y;
+  }
+  for (uint32_t arc = lo; arc < hi; arc++) {
+    if (match && __ldg(F.ilabel + arc) != il) break;
+    const uint4 pl = __ldg(&F.payload[arc]);
+    if (pl.y != sv) continue;
+    const double w2 = __hiloint2double((int)pl.w, (int)pl.z);
+    const double ew = match ? 0.0 + w2 : w2;   // :189-198 a1.weight (x) a2.weight with a1.weight == One; :258-268 a2.weight
+    if (du + ew == dv) { out.ilabel = il; out.olabel = pl.x; out.weight = ew; return true; }
+  }
+  return false;
+}
+
+template <int G, bool DENSE>
+__device__ inline int32_t search_lean(const SearchParams& p, const LhsBytes& lhs, const LeanArena& a, uint32_t* out_path_len,
+                                      uint64_t* out_pool_off, double* out_final_w, uint32_t* out_n_tuples,
+                                      unsigned long long* out_relax) {
+  const Group<G> g;
+  LeanState st;
+  st.n_tuples = 0; st.chunk_next = 0; st.free_head = kNoChunk; st.bag_len = 0; st.wline = 0; st.occupied = 0; st.last = 0;
+  st.relax_calls = 0; st.low_pending = false; st.overflow = false; st.sorted = false; st.lossy = false;
+  unsigned long long future_min = ~0ull;
+  *out_path_len = 0; *out_pool_off = 0; *out_final_w = d_inf(); *out_n_tuples = 0; *out_relax = 0;
+  const DevFstView& F = p.fst;
+  if (F.start == kNone) return kStNoPath;
+
+  // initial tuple: id 0, dist One, ready at level 0 (compose-shortest-path.zig:146-153)
+  if (g.lane == 0) {
+    const unsigned long long k0 = pack_key(0, F.start, 0);
+    uint32_t pos, id, prev; double d;
+    lean_lookup<DENSE>(a, k0, pos, d, id, prev);
+    pos = lean_claim<DENSE>(a, k0, pos);
+    lean_store<DENSE>(a, pos, k0, 0.0, 0u, kNone);
+    a.key_of[0] = k0;
+  }
+  a.win[g.lane] = g.lane == 0 ? 1u : 0u;   // window = line 0 (all of l0 is zero between strings)
+  st.n_tuples = 1;
+  g.sync();
+
+  bool have_best = false; uint32_t best_id = 0; double best_fw = d_inf(), best_total = d_inf();
+  double cur_dist = 0.0;
+
+  for (;;) {
+    if (st.overflow) break;
+    // ── pop the smallest ready id (:159-163; the set only holds unsettled tuples at the level distance) ──
+    if (st.low_pending) { lean_window_evict<G>(g, a, st); st.low_pending = false; }
+    const uint32_t w = a.win[g.lane];
+    const unsigned bal = g.ballot(w != 0);
+    if (bal == 0) {
+      if (lean_window_next<G>(g, a, st)) continue;
+      if (!lean_advance_level<G, DENSE>(p, g, a, st, have_best, best_total, future_min)) break;
+      cur_dist = __longlong_as_double((long long)st.last);
+      continue;
+    }
+    const int src = __ffs(bal) - 1;
+    const uint32_t ww = g.shfl(w, src);
+    const uint32_t cur_id = ((st.wline * G + src) << 5) + (__ffs(ww) - 1);
+    if ((int)g.lane == src) a.win[src] = ww & (ww - 1);
+    g.sync();
+    const unsigned long long ckey = a.key_of[cur_id];
+    const uint32_t s1 = (uint32_t)(ckey >> 34), s2 = (uint32_t)(ckey >> 2);
+
+    // final check (:165-179): only the last state of the string acceptor is final, weight One
+    if (s1 == lhs.len) {
+      const double fw2 = F.final_w[s2];
+      if (!d_isinf(fw2)) {
+        const double final_w = 0.0 + fw2;
+        const double total = cur_dist + final_w;
+        if (!have_best || total < best_total || (total == best_total && cur_id < best_id)) {
+          have_best = true; best_id = cur_id; best_fw = final_w; best_total = total;
+        }
+      }
+    }
+    // ── expansion (:182-202 match arcs, then :254-278 input-epsilon arcs; filter is 0 or 1 here) ──
+    const uint4 rec = __ldg(&F.state_rec[s2]);   // {arc_begin, eps_end, arc_end}
+    const uint32_t deg = rec.z - rec.x;
+    const uint32_t x = s1 < lhs.len ? (uint32_t)__ldg(lhs.s + s1) + 1u : 0xFFFFFFFEu;
+    if (deg <= (uint32_t)G) {
+      const uint32_t arc = rec.x + g.lane;
+      const bool valid = g.lane < deg;
+      uint32_t il = 0xFFFFFFFFu;
+      uint4 pl = make_uint4(0, 0, 0, 0);
+      if (valid) { il = __ldg(F.ilabel + arc); pl = __ldg(&F.payload[arc]); }
+      const bool is_match = valid && il == x;
+      const bool is_eps = valid && arc < rec.y;
+      const double w2 = __hiloint2double((int)pl.w, (int)pl.z);
+      const double ew = is_match ? 0.0 + w2 : w2;
+      const unsigned long long K = is_match ? pack_key(s1 + 1u, pl.y, 0u) : pack_key(s1, pl.y, 1u);
+      const unsigned first = g.ballot(is_match);
+      lean_relax<G, DENSE>(p, g, a, st, cur_id, cur_dist, is_match || is_eps, K, ew, first, future_min);
+    } else {
+      uint32_t lo = 0, hi = 0;
+      if (s1 < lhs.len) equal_range(g, F.ilabel, rec.x, rec.z, x, lo, hi);
+      for (uint32_t cb = lo; cb < hi && !st.overflow; cb += G) {
+        const bool active = cb + g.lane < hi;
+        uint4 pl = make_uint4(0, 0, 0, 0);
+        if (active) pl = __ldg(&F.payload[cb + g.lane]);
+        lean_relax<G, DENSE>(p, g, a, st, cur_id, cur_dist, active, pack_key(s1 + 1u, pl.y, 0u), 0.0 + __hiloint2double((int)pl.w, (int)pl.z),
+                             Group<G>::kBits, future_min);
+        g.sync();
+      }
+      for (uint32_t cb = rec.x; cb < rec.y && !st.overflow; cb += G) {
+        const bool active = cb + g.lane < rec.y;
+        uint4 pl = make_uint4(0, 0, 0, 0);
+        if (active) pl = __ldg(&F.payload[cb + g.lane]);
+        lean_relax<G, DENSE>(p, g, a, st, cur_id, cur_dist, active, pack_key(s1, pl.y, 1u), __hiloint2double((int)pl.w, (int)pl.z),
+                             Group<G>::kBits, future_min);
+        g.sync();
+      }
+    }
+  }
+
+  int32_t status = kStPath;
+  uint32_t plen = 0;
+  unsigned long long poff = 0;
+  uint32_t* scratch = a.bag;   // the future set is dead now; bag_cap >= tuple_cap by construction
+  if (st.overflow) {
+    status = kStRetry;
+  } else if (!have_best) {
+    status = kStNoPath;                                               // :368-370
+  } else {
+    if (g.lane == 0) {                                                // :372-380 back-track (ids only)
+      uint32_t cur = best_id;
+      while (cur != 0) {
+        uint32_t pos, id, prev; double d;
+        lean_lookup<DENSE>(a, a.key_of[cur], pos, d, id, prev);
+        if (prev == kNone) { status = kStNoPath; break; }             // :375-377
+        if (plen >= st.n_tuples) { status = kStCycle; break; }        // hazard H1 (reference: out of memory)
+        scratch[plen++] = cur;
+        cur = prev;
+      }
+      if (status == kStPath && plen > 0) {
+        poff = atomicAdd(p.pool_cursor, (unsigned long long)plen);
+        if (poff + plen > p.pool_cap) status = kStRetry;
+      }
+    }
+    g.sync();
+    status = g.shfl(status, 0); plen = g.shfl(plen, 0); poff = g.shfl(poff, 0);
+    if (status == kStPath) {
+      bool bad = false;
+      for (uint32_t i = g.lane; i < plen; i += G) {
+        const unsigned long long Kv = a.key_of[scratch[i]];
+        uint32_t pos, id, prev, id2, prev2; double dv, du;
+        lean_lookup<DENSE>(a, Kv, pos, dv, id, prev);
+        const unsigned long long Ku = a.key_of[prev];
+        lean_lookup<DENSE>(a, Ku, pos, du, id2, prev2);
+        PoolArc pa; pa.ilabel = 0; pa.olabel = 0; pa.weight = 0.0;
+        if (!lean_recover_arc(F, lhs, Ku, Kv, du, dv, pa)) bad = true;
+        p.pool[poff + i] = pa;
+      }
+      if (g.any(bad)) { status = kStInternal; plen = 0; }
+    } else {
+      plen = 0;
+    }
+  }
+  // Restore the arena invariants for the next string: table untouched-state, bitmaps zero.
+  g.sync();
+  const uint32_t n = st.n_tuples;
+  if (DENSE) {
+    if ((uint64_t)n * 4 < a.tab_entries) {
+      for (uint32_t i = g.lane; i < n; i += G)
+        *reinterpret_cast<uint4*>(a.tab + (uint64_t)lean_dense_index<true>(a, a.key_of[i]) * 16) = make_uint4(~0u, ~0u, ~0u, ~0u);
+    } else {
+      uint4* t = reinterpret_cast<uint4*>(a.tab);
+      for (uint64_t i = g.lane; i < a.tab_entries; i += G) t[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+    }
+  } else {
+    // two phases: resolve every tuple's slot first (probing needs intact chains), then clear
+    uint32_t* slot_tmp = reinterpret_cast<uint32_t*>(a.key_of);
+    for (uint32_t base = 0; base < n; base += G) {
+      const uint32_t i = base + g.lane;
+      uint32_t sl = 0, id, prev; double d;
+      if (i < n) lean_lookup<false>(a, a.key_of[i], sl, d, id, prev);
+      g.sync();                        // all keys of this stripe are read before any is overwritten
+      if (i < n) slot_tmp[i] = sl;     // aliases key_of[i/2]: only stripes already resolved
+      g.sync();
+    }
+    LeanSlot* tab = reinterpret_cast<LeanSlot*>(a.tab);
+    for (uint32_t i = g.lane; i < n; i += G) tab[slot_tmp[i]].key = kEmptyKey;
+  }
+  if (st.overflow) {
+    // aborted searches can leave ready bits behind
+    for (uint32_t i = g.lane; i < ((n + 32u * G - 1) / (32u * G)) * G; i += G) a.l0[i] = 0;
+    for (uint32_t i = g.lane; i < a.n1; i += G) a.l1[i] = 0;
+    a.win[g.lane] = 0;
+  }
+  g.sync();
+  *out_path_len = plen; *out_pool_off = poff; *out_final_w = (status == kStPath) ? best_fw : d_inf();
+  *out_n_tuples = st.n_tuples; *out_relax = st.relax_calls;
+  return status;
+}
+
+template <int G>
+__device__ inline LeanArena lean_arena_at(const SearchParams& p, uint32_t slot_idx, uint32_t* smem_grp) {
+  const LeanLayout L = lean_layout(G, p.dense != 0, p.tab_entries, p.tuple_cap, p.heap_cap, p.bag_cap);
+  uint8_t* base = p.arena + (uint64_t)slot_idx * p.arena_stride;
+  LeanArena a;
+  a.tab = base + L.off_tab;
+  a.key_of = reinterpret_cast<unsigned long long*>(base + L.off_keyof);
+  a.l0 = reinterpret_cast<uint32_t*>(base + L.off_l0);
+  a.bag = reinterpret_cast<uint32_t*>(base + L.off_bag);
+  a.chunks = reinterpret_cast<uint32_t*>(base + L.off_chunks);
+  a.bucket = reinterpret_cast<uint2*>(smem_grp);
+  a.win = smem_grp + 128; a.l1 = a.win + G;
+  a.tab_entries = p.tab_entries; a.S = p.fst.num_states;
+  a.tuple_cap = p.tuple_cap; a.chunk_cap = p.heap_cap; a.bag_cap = p.bag_cap; a.n1 = L.n1;
+  const unsigned lane = (threadIdx.x & 31u) % G;
+  for (uint32_t i = lane; i < L.smem_words - 128; i += G) a.win[i] = 0;
+  __syncwarp();
+  return a;
+}
+
+// Persistent batch kernel: every G-lane group pulls strings from a global queue.
+template <int G, bool DENSE>
+__global__ void __launch_bounds__(128) csp_batch_lean_kernel(SearchParams p) {
+  extern __shared__ __align__(16) uint32_t smem_all[];
+  const Group<G> g;
+  const uint32_t gib = threadIdx.x / G;
+  const uint32_t gslot = blockIdx.x * (blockDim.x / G) + gib;
+  const LeanLayout L = lean_layout(G, DENSE, p.tab_entries, p.tuple_cap, p.heap_cap, p.bag_cap);
+  const LeanArena a = lean_arena_at<G>(p, gslot, smem_all + (size_t)gib * L.smem_words);
+  unsigned long long relax_total = 0, tuple_total = 0;
+  for (;;) {
+    uint32_t item = 0;
+    if (g.lane == 0) item = atomicAdd(p.queue_head, 1u);
+    item = g.shfl(item, 0);
+    if (item >= p.n_items) break;
+    const uint32_t idx = p.order ? p.order[item] : item;
+    LhsBytes lhs; lhs.s = p.bytes + p.offsets[idx]; lhs.len = (uint32_t)(p.offsets[idx + 1] - p.offsets[idx]);
+    uint32_t plen; uint64_t poff; double fw; uint32_t nt; unsigned long long nr;
+    const int32_t status = search_lean<G, DENSE>(p, lhs, a, &plen, &poff, &fw, &nt, &nr);
+    if (g.lane == 0) {
+      p.status[idx] = status; p.path_len[idx] = plen; p.pool_off[idx] = poff; p.final_w[idx] = fw; p.n_tuples[idx] = nt;
+    }
+    relax_total += nr; tuple_total += nt;
+  }
+  if (g.lane == 0) {
+    if (relax_total) atomicAdd(p.relax_counter, relax_total);
+    if (tuple_total) atomicAdd(p.tuple_counter, tuple_total);
+  }
+}
+
+}  // namespace fstb200

@@ -52,7 +52,7 @@ constexpr uint32_t kSettledBit = 0x80000000u;
 
 // Per-string status written by the search kernel (internal; the C ABI maps
 // kRetry to a retry pass and finally to FST_B200_TOO_LARGE).
-enum : int32_t { kStPath = 0, kStNoPath = 1, kStCycle = 2, kStTooLarge = 3, kStRetry = 100 };
+enum : int32_t { kStPath = 0, kStNoPath = 1, kStCycle = 2, kStTooLarge = 3, kStInternal = 4, kStRetry = 100 };
 
 // Reversed path arc as written to the path pool by the search kernel.
 struct __align__(16) PoolArc { uint32_t ilabel, olabel; double weight; };
@@ -74,6 +74,8 @@ struct SearchParams {
   uint32_t heap_cap;       // binary-heap entries (serial path) / 128-byte chunks (warp path)
   uint32_t bag_cap;        // warp path: unsorted future ids
   uint32_t exhaustive;
+  uint32_t dense;          // lean path: 1 = direct-indexed table, 0 = hash table
+  uint64_t tab_entries;    // lean path: dense records ((max_len+1) * S * 2) or hash slots
   // work queue + counters
   uint32_t* queue_head;
   unsigned long long* pool_cursor;

@@ -15,6 +15,7 @@
 
 #include "csp_kernels.cuh"
 #include "csp_warp.cuh"
+#include "csp_lean.cuh"
 #include "host_fst.hpp"
 
 namespace fstb200 {
@@ -34,6 +35,7 @@ struct Config {
   uint32_t lanes_per_string = 0;
   uint32_t tuples_hint = 0;
   uint32_t exhaustive = 0;
+  uint32_t engine = 0;       // 0 auto, 1 general warp kernel, 2 lean + hash table, 3 lean + dense table
 };
 inline Config& global_config() { static Config c; return c; }
 
@@ -44,6 +46,7 @@ struct DeviceFst {
   void* block = nullptr;   // one allocation holding all arrays
   size_t bytes = 0;
   bool serial = false;     // negative weights: literal sequential relax
+  bool lean_ok = false;    // all arc weights finite and >= 0: the lean batched kernel applies
   uint32_t hint_tuples = 0;  // largest per-string tuple count seen so far (arena sizing)
 };
 
@@ -67,13 +70,15 @@ inline cudaError_t upload_fst(const HostFrozen& f, int device, DeviceFst** out) 
     fin[s] = st[s].final_weight;
     maxdeg = std::max(maxdeg, st[s].num_arcs);
   }
+  bool all_finite = true;
   for (uint32_t a = 0; a < A; a++) {
+    if (std::isinf(ar[a].weight)) all_finite = false;
     il[a] = ar[a].ilabel;
     unsigned long long wb; std::memcpy(&wb, &ar[a].weight, 8);
     pl[a] = make_uint4(ar[a].olabel, ar[a].nextstate, (uint32_t)(wb & 0xFFFFFFFFu), (uint32_t)(wb >> 32));
   }
   auto d = new DeviceFst();
-  d->device = device; d->bytes = total; d->serial = f.has_negative;
+  d->device = device; d->bytes = total; d->serial = f.has_negative; d->lean_ok = !f.has_negative && all_finite;
   cudaError_t e = cudaMalloc(&d->block, total);
   if (e != cudaSuccess) { delete d; return e; }
   e = cudaMemcpy(d->block, h.data(), total, cudaMemcpyHostToDevice);
@@ -159,7 +164,7 @@ class Engine {
 
   // Device-resident batch.  All d_* pointers are device memory on this device.
   // Synchronises `stream` before returning (the retry decision needs a read-back).
-  cudaError_t run_batch(DeviceFst* fst, const uint8_t* d_bytes, const uint64_t* d_offsets, uint32_t n,
+  cudaError_t run_batch(DeviceFst* fst, const uint8_t* d_bytes, const uint64_t* d_offsets, uint32_t n, uint32_t max_len,
                         int32_t* d_status, uint64_t* d_path_offsets, uint32_t* d_il, uint32_t* d_ol, double* d_w,
                         double* d_final, uint32_t* d_ntuples, uint64_t path_capacity,
                         uint64_t* d_out_offsets, uint8_t* d_out_bytes, uint64_t out_capacity,
@@ -179,53 +184,45 @@ class Engine {
     fill_retry_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_status, d_path_len_, n);
     bc->launches++;
 
-    uint32_t G = choose_lanes(cfg, fst);
     uint32_t tuple_cap = cfg.tuples_hint ? cfg.tuples_hint : (fst->hint_tuples ? fst->hint_tuples + fst->hint_tuples / 4 + 64 : 4096);
-    uint32_t n_items = n;
+    uint32_t n_items = n, heap_mult = 1;
     const uint32_t* d_order = nullptr;
+    auto too_large = [&]() {
+      mark_too_large_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_status, d_path_len_, n);
+      bc->launches++;
+    };
     for (uint32_t pass = 0;; pass++) {
       bc->passes++;
-      uint32_t hash_cap, heap_cap, bag_cap, smem_per_warp; uint64_t stride;
-      const bool fast = !fst->serial;
-      if (fast && tuple_cap > kMaxFastTuples) {
-        mark_too_large_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_status, d_path_len_, n);
-        bc->launches++;
-        break;
-      }
-      layout_for(fast, tuple_cap, hash_cap, heap_cap, bag_cap, stride, smem_per_warp);
-      if (fast) G = 32;
-      uint32_t max_groups = max_resident_groups(G, fst->serial, smem_per_warp);
-      uint32_t want = std::min<uint32_t>(n_items, max_groups);
-      uint64_t ws = workspace_budget(cfg);
-      uint32_t fit = (uint32_t)std::min<uint64_t>(ws / stride, 0xFFFFFFFFull);
-      if (fit == 0) {
-        // even one arena does not fit: these strings are too large for the budget
-        mark_too_large_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_status, d_path_len_, n);
-        bc->launches++;
-        break;
-      }
+      Geom gm;
+      if (!geometry(cfg, fst, max_len, tuple_cap, heap_mult, &gm)) { too_large(); break; }
+      const uint32_t max_groups = max_resident_groups(gm);
+      const uint32_t want = std::min<uint32_t>(n_items, max_groups);
+      const uint64_t ws = workspace_budget(cfg);
+      const uint32_t fit = (uint32_t)std::min<uint64_t>(ws / gm.stride, 0xFFFFFFFFull);
+      if (fit == 0) { too_large(); break; }   // even one arena does not fit the budget
       // full 128-thread blocks when the budget allows, else one partial block
-      uint32_t gpb = 128 / G, threads = 128, blocks;
+      uint32_t gpb = 128 / gm.G, threads = 128, blocks;
       if (fit >= gpb) {
         blocks = std::min((want + gpb - 1) / gpb, fit / gpb);
       } else {
-        blocks = 1; gpb = std::min(want, fit); threads = gpb * G;
+        blocks = 1; gpb = std::min(want, fit); threads = gpb * gm.G;
       }
-      FSTB_CUDA(ensure_workspace((uint64_t)blocks * gpb * stride, fast, hash_cap, tuple_cap, heap_cap, bag_cap, stride, blocks * gpb, stream));
+      FSTB_CUDA(ensure_workspace(gm, blocks * gpb, stream));
       bc->launches += init_launches_; init_launches_ = 0;
 
       SearchParams p{};
       p.fst = fst->view;
       p.bytes = d_bytes; p.offsets = d_offsets; p.order = d_order; p.n_items = n_items;
-      p.arena = static_cast<uint8_t*>(d_workspace_); p.arena_stride = stride;
-      p.hash_cap = hash_cap; p.tuple_cap = tuple_cap; p.heap_cap = heap_cap; p.bag_cap = bag_cap; p.exhaustive = cfg.exhaustive;
+      p.arena = static_cast<uint8_t*>(d_workspace_); p.arena_stride = gm.stride;
+      p.hash_cap = gm.hash_cap; p.tuple_cap = gm.tuple_cap; p.heap_cap = gm.heap_cap; p.bag_cap = gm.bag_cap; p.exhaustive = cfg.exhaustive;
+      p.dense = gm.dense ? 1u : 0u; p.tab_entries = gm.tab_entries;
       p.queue_head = d_cnt + 0;
       p.pool_cursor = reinterpret_cast<unsigned long long*>(d_cnt + 2);
       p.relax_counter = reinterpret_cast<unsigned long long*>(d_cnt + 4);
       p.tuple_counter = reinterpret_cast<unsigned long long*>(d_cnt + 6);
       p.status = d_status; p.path_len = d_path_len_; p.pool_off = d_pool_off_; p.final_w = d_final; p.n_tuples = d_ntuples;
       p.pool = d_pool_; p.pool_cap = pool_cap_;
-      launch_search(G, fst->serial, blocks, threads, smem_per_warp, p, stream);
+      launch_search(gm, blocks, threads, p, stream);
       bc->launches++;
       FSTB_CUDA(cudaGetLastError());
       // any string that overflowed its arena (or the pool)?
@@ -241,15 +238,19 @@ class Engine {
       if (pool_used > pool_cap_) {
         // path pool too small: report the requirement; caller grows and re-runs
         bc->path_required = pool_used;
-        mark_too_large_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_status, d_path_len_, n);
-        bc->launches++;
+        too_large();
         break;
       }
-      // next pass: only the overflowed strings, 8x larger arenas
+      // next pass: only the overflowed strings, 8x larger arenas (and a deeper radix-heap pool)
       n_items = retry;
       d_order = d_order_buf_[pass & 1];
-      if (tuple_cap > (1u << 31) / 8) { mark_too_large_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_status, d_path_len_, n); bc->launches++; break; }
-      tuple_cap *= 8;
+      if (gm.kind == kLean && gm.dense && gm.tuple_cap >= gm.tab_entries) {
+        if (heap_mult >= 64) { too_large(); break; }
+        heap_mult *= 4;
+      } else {
+        if (tuple_cap > (1u << 31) / 8) { too_large(); break; }
+        tuple_cap *= 8;
+      }
       FSTB_CUDA(cudaMemsetAsync(d_cnt + 0, 0, 4, stream));   // queue head
     }
 
@@ -327,12 +328,15 @@ class Engine {
     FSTB_CUDA(cudaEventRecord(ev0_, stream));
     for (;;) {
       bc->passes++;
-      uint32_t hash_cap, heap_cap, bag_cap, smem_per_warp; uint64_t stride;
-      const bool fast = !serial;
-      if (fast && tuple_cap > kMaxFastTuples) { *status = kStTooLarge; return cudaSuccess; }
-      layout_for(fast, tuple_cap, hash_cap, heap_cap, bag_cap, stride, smem_per_warp);
-      if (stride > workspace_budget(cfg)) { *status = kStTooLarge; return cudaSuccess; }
-      FSTB_CUDA(ensure_workspace(stride, fast, hash_cap, tuple_cap, heap_cap, bag_cap, stride, 1, stream));
+      Geom gm;
+      Config c1 = cfg; c1.engine = 1;   // a general left operand never takes the lean (byte-string) kernel
+      DeviceFst f1 = *fst; f1.serial = serial;
+      if (!geometry(c1, &f1, 0, tuple_cap, 1, &gm)) { *status = kStTooLarge; return cudaSuccess; }
+      if (gm.stride > workspace_budget(cfg)) { *status = kStTooLarge; return cudaSuccess; }
+      const uint32_t hash_cap = gm.hash_cap, heap_cap = gm.heap_cap, bag_cap = gm.bag_cap, smem_per_warp = gm.smem_per_group;
+      const uint64_t stride = gm.stride;
+      tuple_cap = gm.tuple_cap;
+      FSTB_CUDA(ensure_workspace(gm, 1, stream));
       bc->launches += init_launches_; init_launches_ = 0;
       FSTB_CUDA(cudaMemsetAsync(d_cnt, 0, 64, stream));
       SearchParams p{};
@@ -391,7 +395,7 @@ class Engine {
   }
 
   void release_all() {
-    cudaFree(d_workspace_); d_workspace_ = nullptr; workspace_bytes_ = 0; layout_hash_cap_ = 0;
+    cudaFree(d_workspace_); d_workspace_ = nullptr; workspace_bytes_ = 0; layout_groups_ = 0; budget_cache_ = 0;
     free_scratch();
   }
 
@@ -402,7 +406,7 @@ class Engine {
   cudaEvent_t ev0_{}, ev1_{};
   // workspace (arenas)
   void* d_workspace_ = nullptr; uint64_t workspace_bytes_ = 0;
-  uint32_t layout_hash_cap_ = 0, layout_tuple_cap_ = 0, layout_groups_ = 0; uint64_t layout_stride_ = 0;
+  uint32_t layout_groups_ = 0;
   // per-batch scratch
   uint32_t scratch_n_ = 0;
   uint32_t* d_path_len_ = nullptr; uint64_t* d_pool_off_ = nullptr; uint32_t* d_out_len_ = nullptr; uint64_t* d_len64_ = nullptr;
@@ -412,28 +416,66 @@ class Engine {
   void* d_scan_tmp_ = nullptr; size_t scan_tmp_bytes_ = 0;
 
   uint32_t init_launches_ = 0;
-  bool layout_fast_ = false; uint32_t layout_heap_cap_ = 0;
 
-  // arena geometry for a per-string tuple capacity
-  static void layout_for(bool fast, uint32_t& tuple_cap, uint32_t& hash_cap, uint32_t& heap_cap, uint32_t& bag_cap, uint64_t& stride,
-                         uint32_t& smem_per_warp) {
-    if (fast) {
-      if (tuple_cap < 256) tuple_cap = 256;
-      hash_cap = (uint32_t)std::min<uint64_t>(0xFFFFFFF0ull, (uint64_t)tuple_cap * 100 / 65 + 16);
-      heap_cap = 96 + tuple_cap / 24;     // 128-byte chunks of 31 ids: ~1.3 queued ids per tuple
-      bag_cap = tuple_cap;                // also the back-track scratch (path <= tuples)
-      WarpLayout L = warp_layout(hash_cap, tuple_cap, heap_cap, bag_cap);
-      stride = L.total;
-      smem_per_warp = L.smem_words * 4;
-    } else {
-      hash_cap = 1024;
-      while ((uint64_t)hash_cap * 6 / 10 < tuple_cap && hash_cap < (1u << 31)) hash_cap <<= 1;
-      tuple_cap = (uint32_t)((uint64_t)hash_cap * 6 / 10);
-      heap_cap = tuple_cap * 3;
-      bag_cap = 0;
-      stride = arena_bytes(hash_cap, tuple_cap, heap_cap);
-      smem_per_warp = 0;
+  enum { kSerial = 0, kWarp = 1, kLean = 2 };
+  // Arena geometry of one pass: which kernel, and every capacity that shapes the arena.
+  struct Geom {
+    int kind = kWarp; uint32_t G = 32; bool dense = false; uint64_t tab_entries = 0;
+    uint32_t hash_cap = 0, tuple_cap = 0, heap_cap = 0, bag_cap = 0, smem_per_group = 0; uint64_t stride = 0;
+    uint64_t off_l0 = 0, tab_bytes = 0, l0_bytes = 0;
+    bool same(const Geom& o) const {
+      return kind == o.kind && G == o.G && dense == o.dense && tab_entries == o.tab_entries && hash_cap == o.hash_cap &&
+             tuple_cap == o.tuple_cap && heap_cap == o.heap_cap && bag_cap == o.bag_cap && stride == o.stride;
     }
+  };
+  static constexpr uint64_t kDenseLimitBytes = 96ull << 20;   // per-string dense table budget
+  Geom layout_;
+
+  static bool geometry(const Config& cfg, const DeviceFst* fst, uint32_t max_len, uint32_t tuple_cap, uint32_t heap_mult, Geom* g) {
+    *g = Geom();
+    if (fst->serial) {
+      g->kind = kSerial; g->G = choose_lanes(cfg, fst);
+      uint32_t hash_cap = 1024;
+      while ((uint64_t)hash_cap * 6 / 10 < tuple_cap && hash_cap < (1u << 31)) hash_cap <<= 1;
+      g->hash_cap = hash_cap; g->tuple_cap = (uint32_t)((uint64_t)hash_cap * 6 / 10);
+      g->heap_cap = g->tuple_cap * 3; g->bag_cap = 0;
+      g->stride = arena_bytes(g->hash_cap, g->tuple_cap, g->heap_cap);
+      return true;
+    }
+    if (tuple_cap < 256) tuple_cap = 256;
+    const bool lean = fst->lean_ok && cfg.engine != 1;
+    if (!lean) {
+      if (tuple_cap > kMaxFastTuples) return false;
+      g->kind = kWarp; g->G = 32; g->tuple_cap = tuple_cap;
+      g->hash_cap = (uint32_t)std::min<uint64_t>(0xFFFFFFF0ull, (uint64_t)tuple_cap * 100 / 65 + 16);
+      g->heap_cap = 96 + (tuple_cap / 24) * heap_mult;   // 128-byte chunks of 31 ids: ~1.3 queued ids per tuple
+      g->bag_cap = tuple_cap;                             // also the back-track scratch (path <= tuples)
+      WarpLayout L = warp_layout(g->hash_cap, g->tuple_cap, g->heap_cap, g->bag_cap);
+      g->stride = L.total; g->smem_per_group = L.smem_words * 4;
+      return true;
+    }
+    g->kind = kLean; g->G = cfg.lanes_per_string == 16 ? 16 : 32;
+    const uint64_t E = (uint64_t)(max_len + 1) * fst->view.num_states * 2;
+    const bool dense_ok = E < 0xFFFFFF00ull && E * 16 <= kDenseLimitBytes;
+    // dense pays when the search touches a good part of the (position x state) grid; a small search keeps its
+    // hash table in cache instead
+    const uint64_t hash_bytes = (uint64_t)tuple_cap * 50;
+    g->dense = cfg.engine == 3 ? dense_ok : (cfg.engine == 2 ? false : dense_ok && (E * 16 <= 8 * hash_bytes || E * 16 <= (256u << 10)));
+    if (g->dense) {
+      if ((uint64_t)tuple_cap > E) tuple_cap = (uint32_t)E;
+      g->tab_entries = E; g->hash_cap = 0;
+    } else {
+      g->hash_cap = (uint32_t)std::min<uint64_t>(0xFFFFFFF0ull, (uint64_t)tuple_cap * 100 / 65 + 16);
+      g->tab_entries = g->hash_cap;
+    }
+    if (tuple_cap > kMaxFastTuples) return false;
+    g->tuple_cap = tuple_cap;
+    g->heap_cap = 96 + (tuple_cap / 24) * heap_mult;
+    g->bag_cap = tuple_cap;
+    LeanLayout L = lean_layout((int)g->G, g->dense, g->tab_entries, g->tuple_cap, g->heap_cap, g->bag_cap);
+    g->stride = L.total; g->smem_per_group = L.smem_words * 4;
+    g->off_l0 = L.off_l0; g->tab_bytes = L.tab_bytes; g->l0_bytes = L.l0_bytes;
+    return true;
   }
 
   static uint32_t choose_lanes(const Config& cfg, const DeviceFst* fst) {
@@ -445,26 +487,33 @@ class Engine {
     return 8;
   }
 
-  uint32_t max_resident_groups(uint32_t G, bool serial, uint32_t smem_per_warp) {
-    int bps = 0;
-    const void* fn = serial ? kernel_ptr(G) : (const void*)csp_batch_warp_kernel;
-    const size_t sm = serial ? 0 : (size_t)smem_per_warp * 4;
-    if (!serial && sm > 40 * 1024) cudaFuncSetAttribute(csp_batch_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, 128, sm) != cudaSuccess || bps <= 0) bps = 1;
-    return (uint32_t)bps * (uint32_t)sm_count * (128 / G);
-  }
-  static const void* kernel_ptr(uint32_t G) {
-    switch (G) { case 32: return (const void*)csp_batch_kernel<32, true>; case 16: return (const void*)csp_batch_kernel<16, true>;
-                 case 8: return (const void*)csp_batch_kernel<8, true>; default: return (const void*)csp_batch_kernel<4, true>; }
-  }
-  static void launch_search(uint32_t G, bool serial, uint32_t blocks, uint32_t threads, uint32_t smem_per_warp, const SearchParams& p,
-                            cudaStream_t s) {
-    if (serial) {
-      switch (G) { case 32: csp_batch_kernel<32, true><<<blocks, threads, 0, s>>>(p); break; case 16: csp_batch_kernel<16, true><<<blocks, threads, 0, s>>>(p); break;
-                   case 8: csp_batch_kernel<8, true><<<blocks, threads, 0, s>>>(p); break; default: csp_batch_kernel<4, true><<<blocks, threads, 0, s>>>(p); break; }
-    } else {
-      csp_batch_warp_kernel<<<blocks, threads, (size_t)(threads / 32) * smem_per_warp, s>>>(p);
+  static const void* kernel_ptr(const Geom& g) {
+    if (g.kind == kWarp) return (const void*)csp_batch_warp_kernel;
+    if (g.kind == kLean) {
+      if (g.G == 16) return g.dense ? (const void*)csp_batch_lean_kernel<16, true> : (const void*)csp_batch_lean_kernel<16, false>;
+      return g.dense ? (const void*)csp_batch_lean_kernel<32, true> : (const void*)csp_batch_lean_kernel<32, false>;
     }
+    switch (g.G) { case 32: return (const void*)csp_batch_kernel<32, true>; case 16: return (const void*)csp_batch_kernel<16, true>;
+                   case 8: return (const void*)csp_batch_kernel<8, true>; default: return (const void*)csp_batch_kernel<4, true>; }
+  }
+  uint32_t max_resident_groups(const Geom& g) {
+    int bps = 0;
+    const void* fn = kernel_ptr(g);
+    const size_t sm = (size_t)g.smem_per_group * (128 / g.G);
+    if (sm > 40 * 1024) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, 128, sm) != cudaSuccess || bps <= 0) bps = 1;
+    return (uint32_t)bps * (uint32_t)sm_count * (128 / g.G);
+  }
+  static void launch_search(const Geom& g, uint32_t blocks, uint32_t threads, const SearchParams& p, cudaStream_t s) {
+    const size_t sm = (size_t)(threads / g.G) * g.smem_per_group;
+    if (g.kind == kWarp) { csp_batch_warp_kernel<<<blocks, threads, sm, s>>>(p); return; }
+    if (g.kind == kLean) {
+      if (g.G == 16) { if (g.dense) csp_batch_lean_kernel<16, true><<<blocks, threads, sm, s>>>(p); else csp_batch_lean_kernel<16, false><<<blocks, threads, sm, s>>>(p); }
+      else { if (g.dense) csp_batch_lean_kernel<32, true><<<blocks, threads, sm, s>>>(p); else csp_batch_lean_kernel<32, false><<<blocks, threads, sm, s>>>(p); }
+      return;
+    }
+    switch (g.G) { case 32: csp_batch_kernel<32, true><<<blocks, threads, 0, s>>>(p); break; case 16: csp_batch_kernel<16, true><<<blocks, threads, 0, s>>>(p); break;
+                   case 8: csp_batch_kernel<8, true><<<blocks, threads, 0, s>>>(p); break; default: csp_batch_kernel<4, true><<<blocks, threads, 0, s>>>(p); break; }
   }
 
   uint64_t workspace_budget(const Config& cfg) {
@@ -472,34 +521,38 @@ class Engine {
     if (budget_cache_) return budget_cache_;
     size_t fr = 0, tot = 0;
     if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) return 1ull << 30;
-    budget_cache_ = (uint64_t)((fr + workspace_bytes_) * 0.6);
+    budget_cache_ = (uint64_t)((fr + workspace_bytes_) * 0.85);
     return budget_cache_;
   }
   uint64_t budget_cache_ = 0;
 
-  cudaError_t ensure_workspace(uint64_t bytes, bool fast, uint32_t hash_cap, uint32_t tuple_cap, uint32_t heap_cap, uint32_t bag_cap,
-                               uint64_t stride, uint32_t groups, cudaStream_t s) {
+  cudaError_t ensure_workspace(const Geom& g, uint32_t groups, cudaStream_t s) {
+    const uint64_t bytes = (uint64_t)groups * g.stride;
     if (bytes > workspace_bytes_) {
       if (d_workspace_) { FSTB_CUDA(cudaStreamSynchronize(s)); FSTB_CUDA(cudaFree(d_workspace_)); d_workspace_ = nullptr; workspace_bytes_ = 0; }
       FSTB_CUDA(cudaMalloc(&d_workspace_, bytes));
       workspace_bytes_ = bytes;
-      layout_hash_cap_ = 0;
+      layout_groups_ = 0;
     }
-    // Arena invariants (table keys empty, ready bitmap zero) hold after every kernel for
-    // the layout in use; re-initialise only when the layout changes.
-    if (fast != layout_fast_ || hash_cap != layout_hash_cap_ || tuple_cap != layout_tuple_cap_ || heap_cap != layout_heap_cap_ ||
-        stride != layout_stride_ || groups > layout_groups_) {
-      if (fast) {
-        uint64_t words = ((uint64_t)hash_cap * 4 + tuple_cap / 60 + 64) * groups;
+    // Arena invariants (table empty, ready bitmap zero) hold after every kernel for the
+    // geometry in use; re-initialise only when the geometry changes.
+    if (!g.same(layout_) || groups > layout_groups_) {
+      if (g.kind == kWarp) {
+        uint64_t words = ((uint64_t)g.hash_cap * 4 + g.tuple_cap / 60 + 64) * groups;
         uint32_t blocks = (uint32_t)std::min<uint64_t>((words + 255) / 256, (uint64_t)sm_count * 32);
-        warp_arena_init_kernel<<<blocks, 256, 0, s>>>(static_cast<uint8_t*>(d_workspace_), stride, groups, hash_cap, tuple_cap, heap_cap, bag_cap);
+        warp_arena_init_kernel<<<blocks, 256, 0, s>>>(static_cast<uint8_t*>(d_workspace_), g.stride, groups, g.hash_cap, g.tuple_cap, g.heap_cap, g.bag_cap);
+        init_launches_++;
+        FSTB_CUDA(cudaGetLastError());
+      } else if (g.kind == kLean) {
+        uint64_t vecs = (g.tab_bytes + g.l0_bytes) / 16 * groups;
+        uint32_t blocks = (uint32_t)std::min<uint64_t>((vecs + 255) / 256, (uint64_t)sm_count * 32);
+        lean_arena_init_kernel<<<blocks, 256, 0, s>>>(static_cast<uint8_t*>(d_workspace_), g.stride, groups, g.off_l0, g.tab_bytes, g.l0_bytes);
         init_launches_++;
         FSTB_CUDA(cudaGetLastError());
       } else {
         FSTB_CUDA(cudaMemsetAsync(d_workspace_, 0xFF, bytes, s));
       }
-      layout_fast_ = fast; layout_hash_cap_ = hash_cap; layout_tuple_cap_ = tuple_cap; layout_heap_cap_ = heap_cap;
-      layout_stride_ = stride; layout_groups_ = groups;
+      layout_ = g; layout_groups_ = groups;
     }
     return cudaSuccess;
   }

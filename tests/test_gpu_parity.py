@@ -253,3 +253,63 @@ def test_cycle_hazard_is_reported(L, O, gpu):
     res = L.compose_frozen_shortest_path_batch(fprod, data, offsets)
     assert res.status[0] == L.CYCLE
     assert L.compose_frozen_shortest_path(L.MutableFst.compile_string(s), fprod, 1) is None   # reference: OOM -> invalid handle
+
+
+@pytest.mark.parametrize("engine,lanes", [(1, 0), (2, 32), (2, 16), (3, 32), (3, 16)])
+def test_engines_agree(L, O, gpu, engine, lanes):
+    """Every kernel choice for byte-string batches (general warp kernel, lean + hash table, lean + dense table;
+    32 or 16 lanes per string) must reproduce the oracle bit for bit, in early-exit and exhaustive mode."""
+    rng = random.Random(555 + engine)
+    cases = []
+    for case in range(25):
+        spec = random_rhs(rng, real=(case % 3 == 2))
+        fprod, forc, _ = frozen_pair(L, O, spec)
+        cases.append((fprod, forc, [random_string(rng, max_len=9) for _ in range(40)]))
+    # high-degree states: multi-chunk expansions and the binary-searched match range
+    n = 5
+    arcs = []
+    for s in range(n):
+        for _ in range(rng.randint(40, 200)):
+            il = 0 if rng.random() < 0.1 else rng.randint(1, 30)
+            arcs.append((s, il, rng.randint(0, 5), float(rng.randint(0, 2)), rng.randrange(n)))
+    fprod, forc, _ = frozen_pair(L, O, Spec(n, 0, [0.0 if rng.random() < 0.5 else None for _ in range(n)], arcs))
+    cases.append((fprod, forc, [bytes(rng.randint(0, 29) for _ in range(rng.randint(0, 5))) for _ in range(50)]))
+    for kind, lens in ((2, [0, 1, 11, 33, 96]), (1, [0, 5, 11, 19]), (0, [7, 96])):
+        img = gen_image(O, kind, 4096 if kind != 1 else 512, 12)
+        strings = [bytes(i % 12 for i in range(k)) if kind == 0 else bytes(k) for k in lens]
+        cases.append((L.Fst.from_image(img), O.Frozen.from_bytes(img), strings))
+    try:
+        for exhaustive in (0, 1):
+            L.configure(engine=engine, lanes_per_string=lanes, exhaustive=exhaustive)
+            for fprod, forc, strings in cases:
+                res = assert_batch_matches_oracle(L, O, fprod, forc, strings)
+                if exhaustive:
+                    for i, s in enumerate(strings):
+                        p = O.csp_bytes(forc, s)
+                        if p.status == O.STATUS_OK:
+                            assert res.n_tuples[i] == p.tuples
+    finally:
+        L.configure()
+
+
+def test_lean_window_eviction_and_levels(L, O, gpu):
+    """Searches with more than one ready-bitmap line (> 1024 ids), many distance levels and queue jumps
+    (an old tuple lowered to the current level below the window) on both lean tables."""
+    rng = random.Random(2026)
+    n = 60
+    arcs = []
+    for s in range(n):
+        for _ in range(rng.randint(2, 6)):
+            il = 0 if rng.random() < 0.25 else rng.randint(1, 2)
+            arcs.append((s, il, rng.randint(0, 3), float(rng.choice([0, 0, 0, 1, 2, 5])), rng.randrange(n)))
+    fprod, forc, _ = frozen_pair(L, O, Spec(n, 0, [0.0 if rng.random() < 0.3 else None for _ in range(n)], arcs))
+    strings = [bytes(rng.randint(0, 1) for _ in range(rng.randint(20, 60))) for _ in range(24)]
+    try:
+        for engine, lanes in ((2, 32), (3, 32), (3, 16), (2, 16)):
+            for exhaustive in (1, 0):
+                L.configure(engine=engine, lanes_per_string=lanes, exhaustive=exhaustive)
+                res = assert_batch_matches_oracle(L, O, fprod, forc, strings)
+                if exhaustive:
+                    assert max(res.n_tuples) > 1100
+    finally:
+        L.configure()
