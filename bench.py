@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=0, help="strings per GPU per step (0 = workload default)")
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--exhaustive", type=int, default=0)
+    ap.add_argument("--tuples-hint", type=int, default=0, help="expected tuples per string (0 = adaptive: learnt in warm-up)")
     ap.add_argument("--engine", type=int, default=0, help="0 auto, 1 general warp kernel, 2 lean+hash, 3 lean+dense")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -165,7 +166,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L.load()
-    L.configure(lanes_per_string=args.lanes, exhaustive=args.exhaustive, engine=args.engine)
+    L.configure(lanes_per_string=args.lanes, exhaustive=args.exhaustive, engine=args.engine, tuples_hint=args.tuples_hint)
 
     from libfst_b200 import synth
     fst = synth.TRANSDUCERS[args.workload](args.transducer_len, args.branches).freeze()

@@ -8,7 +8,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-SO = os.path.join(HERE, "libfst_b200.so")
+SO = os.environ.get("LIBFST_B200_SO") or os.path.join(HERE, "libfst_b200.so")   # override: tuning variants
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -30,13 +30,14 @@ def is_stale() -> bool:
     return any(os.path.getmtime(s) > t for s in sources())
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str | None = None) -> str:
+    so = out or SO
+    if not force and not is_stale() and out is None:
         return SO
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: libfst_b200 has no CPU build")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", SO, os.path.join(CSRC, "c_api.cu")]
+    cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-o", so, os.path.join(CSRC, "c_api.cu")]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -44,7 +45,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
     if verbose:
         print(r.stderr)
-    return SO
+    return so
 
 
 if __name__ == "__main__":

@@ -19,12 +19,17 @@
 //     strictly smaller distance, or on a tie smaller (ilabel, olabel), impossible
 //     in frozen arc order).  The back-track recomputes it for the P path arcs
 //     instead of storing it for all N tuples.
-//   * FOLD WITHOUT LOOPS.  Candidates of one expansion that hit the same target
-//     are grouped with MATCH.ANY; the minimum new distance of each group is two
-//     REDUX.MIN over the peers (distances are >= +0.0, so the IEEE bit pattern
-//     orders like the value); the first lane of the group applies the take rule
-//     once.  Equivalent to relaxing the candidates one by one in arc order
-//     (DESIGN.md §exactness-fold).
+//   * FOLD, DONE AT UPLOAD.  Arcs of one transducer state with the same (ilabel,
+//     nextstate) always relax the same compose tuple from the same source, and
+//     relaxing them one by one in arc order ends in the same table state as one
+//     relaxation with the smallest weight by the first of them (DESIGN.md
+//     §exactness-fold; fl(c + w) is monotone in w, so min over arcs of the new
+//     distance is the new distance of the min weight).  The search records
+//     `sarc` (device_types.cuh) carry that: {ilabel, nextstate | dup, wmin} — one
+//     16-byte load per lane per pop, no run-time grouping.  (Run-time grouping
+//     was measured first: REDUX.MIN over per-target masks is serialised per mask
+//     by the compiler — 46 % of all executed instructions; MATCH.ANY + a shuffle
+//     gather still cost 38 % of the instructions and the longest stall.)
 //   * READY SET.  Bitmap over discovery ids, 32 ids per word, in HBM; the line
 //     (G words = 32*G ids) that holds the current minimum lives in shared memory
 //     (the WINDOW) and a one-bit-per-line summary sits above it.  The reference's
@@ -37,6 +42,11 @@
 #pragma once
 #include "csp_kernels.cuh"
 #include "csp_warp.cuh"   // kChunkIds, kNoChunk, kMaxFastTuples, bucket_of
+
+// Resident 128-thread blocks per SM the lean kernel is compiled for (register cap = 65536 / (128 * this)).
+#ifndef FSTB_LEAN_MINBLOCKS
+#define FSTB_LEAN_MINBLOCKS 8
+#endif
 
 namespace fstb200 {
 
@@ -114,10 +124,19 @@ template <int G> struct LgG { static constexpr int v = G == 32 ? 5 : (G == 16 ? 
 
 __device__ __forceinline__ uint32_t ldcg_u32(const uint32_t* p) { return __ldcg(p); }
 
+// Tuple key of the lean path: high word = string position p, low word = (transducer state << 1) | filter
+// (filter is 0 or 1 for an epsilon-free left operand; states < 2^31 is checked at upload).  Packing and
+// unpacking are register moves.
+__device__ __forceinline__ unsigned long long lean_key(uint32_t p, uint32_t s, uint32_t f) {
+  return ((unsigned long long)p << 32) | (unsigned long long)((s << 1) | f);
+}
+__device__ __forceinline__ uint32_t lean_key_p(unsigned long long K) { return (uint32_t)(K >> 32); }
+__device__ __forceinline__ uint32_t lean_key_s(unsigned long long K) { return (uint32_t)K >> 1; }
+
 // ── table access ──
 template <bool DENSE>
 __device__ __forceinline__ uint32_t lean_dense_index(const LeanArena& a, unsigned long long K) {
-  return (((uint32_t)(K >> 34)) * a.S + (uint32_t)(K >> 2)) * 2u + (uint32_t)(K & 1u);
+  return (uint32_t)(K >> 32) * (a.S * 2u) + (uint32_t)K;
 }
 // Find the record of key K: position and contents; id == kNone <=> not present (hash: `pos` is then the
 // empty slot that ended the probe — pass it to lean_claim before storing).
@@ -377,39 +396,28 @@ __device__ __forceinline__ bool lean_advance_level(const SearchParams& p, const 
   return false;
 }
 
-// ── one relaxation candidate per lane ──
-// `first`: lanes that precede the other active lanes in the reference's expansion
-// order (match arcs :182-202 before input-epsilon arcs :254-278); only used to
-// number newly discovered tuples.
+// ── one relaxation per lane ──
+// `active` lanes hold DISTINCT targets (the static search records fold parallel arcs, see
+// device_types.cuh `sarc`); `cand` lanes are all arcs of the expansion (the reference's relax calls).
+// `first`: lanes that precede the other lanes in the reference's expansion order (match arcs
+// :182-202 before input-epsilon arcs :254-278); only used to number newly discovered tuples.
 template <int G, bool DENSE>
 __device__ __forceinline__ void lean_relax(const SearchParams& p, const Group<G>& g, const LeanArena& a, LeanState& st, uint32_t cur_id,
-                                           double cur_dist, bool active, unsigned long long K, double ew, unsigned first,
+                                           double cur_dist, bool cand, bool active, unsigned long long K, double wmin, unsigned first,
                                            unsigned long long& future_min) {
-  const unsigned act = g.ballot(active);
-  if (act == 0) return;
-  st.relax_calls += __popc(act);
-  // group by target; the first lane of each group leads
-  unsigned peers;
-  if (DENSE) peers = g.match_any32(active ? lean_dense_index<true>(a, K) : (0xFFFFFF00u | g.lane));
-  else peers = g.match_any(active ? K : (0xFFFFFFFFFFFFFF00ull | g.lane));
-  const unsigned ldr = (unsigned)(__ffs(peers) - 1);
-  const bool leader = active && ldr == g.lane;
-  // minimum new distance over the group (bit pattern order == value order for x >= +0.0)
-  const double nd = cur_dist + ew;
-  const unsigned hi = (unsigned)__double2hiint(nd), lo = (unsigned)__double2loint(nd);
-  const unsigned pm = peers << g.base;
-  const unsigned mhi = __reduce_min_sync(pm, hi);
-  const unsigned mlo = __reduce_min_sync(pm, hi == mhi ? lo : 0xFFFFFFFFu);
-  const double ndmin = __hiloint2double((int)mhi, (int)mlo);
+  const unsigned cm = g.ballot(cand);
+  if (cm == 0) return;
+  st.relax_calls += __popc(cm);
   uint32_t pos = 0, old_id = 0, old_prev = kNone; double old_dist = d_inf();
-  if (leader) lean_lookup<DENSE>(a, K, pos, old_dist, old_id, old_prev);
-  const bool is_new = leader && old_id == kNone;
+  if (active) lean_lookup<DENSE>(a, K, pos, old_dist, old_id, old_prev);
+  const double nd = cur_dist + wmin;   // smallest new distance over the parallel arcs (fl(c + w) is monotone in w)
+  const bool is_new = active && old_id == kNone;
   const unsigned newmask = g.ballot(is_new);
   const uint32_t n_new = __popc(newmask);
   if (st.n_tuples + n_new > a.tuple_cap) { st.overflow = true; return; }
   bool lowered = false;
   uint32_t my_id = old_id;
-  if (leader) {
+  if (active) {
     if (is_new) {
       const unsigned lt = g.lt_mask();
       const bool in_first = (first >> g.lane) & 1u;
@@ -418,13 +426,13 @@ __device__ __forceinline__ void lean_relax(const SearchParams& p, const Group<G>
       a.key_of[my_id] = K;
       pos = lean_claim<DENSE>(a, K, pos);
     }
-    lowered = is_new || ndmin < old_dist;                                                         // :109-114, :137-142
-    const bool take = lowered || (ndmin == old_dist && (old_prev == kNone || cur_id < old_prev)); // :115-126
-    if (take) lean_store<DENSE>(a, pos, K, ndmin, my_id, cur_id);
+    lowered = is_new || nd < old_dist;                                                         // :109-114, :137-142
+    const bool take = lowered || (nd == old_dist && (old_prev == kNone || cur_id < old_prev)); // :115-126
+    if (take) lean_store<DENSE>(a, pos, K, nd, my_id, cur_id);
   }
   st.n_tuples += n_new;
   // queue: ready set if at the current level, else future set
-  const unsigned long long k = (unsigned long long)__double_as_longlong(ndmin);
+  const unsigned long long k = (unsigned long long)__double_as_longlong(nd);
   const bool to_ready = lowered && k == st.last;
   const bool to_future = lowered && k != st.last;
   lean_ready_insert<G>(g, a, st, to_ready, my_id);
@@ -449,7 +457,7 @@ __device__ __forceinline__ void lean_relax(const SearchParams& p, const Group<G>
 // Recover the arc of the step prev -> tuple (see file header).  Returns false if none fits (internal error).
 __device__ inline bool lean_recover_arc(const DevFstView& F, const LhsBytes& lhs, unsigned long long Ku, unsigned long long Kv, double du,
                                         double dv, PoolArc& out) {
-  const uint32_t pu = (uint32_t)(Ku >> 34), su = (uint32_t)(Ku >> 2), pv = (uint32_t)(Kv >> 34), sv = (uint32_t)(Kv >> 2);
+  const uint32_t pu = lean_key_p(Ku), su = lean_key_s(Ku), pv = lean_key_p(Kv), sv = lean_key_s(Kv);
   const uint4 rec = __ldg(&F.state_rec[su]);
   uint32_t lo, hi, il = 0;
   const bool match = pv == pu + 1;
@@ -487,7 +495,7 @@ __device__ inline int32_t search_lean(const SearchParams& p, const LhsBytes& lhs
 
   // initial tuple: id 0, dist One, ready at level 0 (compose-shortest-path.zig:146-153)
   if (g.lane == 0) {
-    const unsigned long long k0 = pack_key(0, F.start, 0);
+    const unsigned long long k0 = lean_key(0, F.start, 0);
     uint32_t pos, id, prev; double d;
     lean_lookup<DENSE>(a, k0, pos, d, id, prev);
     pos = lean_claim<DENSE>(a, k0, pos);
@@ -519,7 +527,7 @@ __device__ inline int32_t search_lean(const SearchParams& p, const LhsBytes& lhs
     if ((int)g.lane == src) a.win[src] = ww & (ww - 1);
     g.sync();
     const unsigned long long ckey = a.key_of[cur_id];
-    const uint32_t s1 = (uint32_t)(ckey >> 34), s2 = (uint32_t)(ckey >> 2);
+    const uint32_t s1 = lean_key_p(ckey), s2 = lean_key_s(ckey);
 
     // final check (:165-179): only the last state of the string acceptor is final, weight One
     if (s1 == lhs.len) {
@@ -537,35 +545,36 @@ __device__ inline int32_t search_lean(const SearchParams& p, const LhsBytes& lhs
     const uint32_t deg = rec.z - rec.x;
     const uint32_t x = s1 < lhs.len ? (uint32_t)__ldg(lhs.s + s1) + 1u : 0xFFFFFFFEu;
     if (deg <= (uint32_t)G) {
+      // one lane per arc of the state, in frozen order (epsilon prefix first)
       const uint32_t arc = rec.x + g.lane;
       const bool valid = g.lane < deg;
-      uint32_t il = 0xFFFFFFFFu;
-      uint4 pl = make_uint4(0, 0, 0, 0);
-      if (valid) { il = __ldg(F.ilabel + arc); pl = __ldg(&F.payload[arc]); }
-      const bool is_match = valid && il == x;
+      uint4 sa = make_uint4(0xFFFFFFFFu, 0x80000000u, 0, 0);
+      if (valid) sa = __ldg(&F.sarc[arc]);
+      const bool is_match = sa.x == x;               // invalid lanes hold ilabel 0xFFFFFFFF, x is never that
       const bool is_eps = valid && arc < rec.y;
-      const double w2 = __hiloint2double((int)pl.w, (int)pl.z);
-      const double ew = is_match ? 0.0 + w2 : w2;
-      const unsigned long long K = is_match ? pack_key(s1 + 1u, pl.y, 0u) : pack_key(s1, pl.y, 1u);
+      const bool cand = is_match || is_eps;
+      const uint32_t nxt = sa.y & 0x7FFFFFFFu;
+      const unsigned long long K = is_match ? lean_key(s1 + 1u, nxt, 0u) : lean_key(s1, nxt, 1u);
       const unsigned first = g.ballot(is_match);
-      lean_relax<G, DENSE>(p, g, a, st, cur_id, cur_dist, is_match || is_eps, K, ew, first, future_min);
+      lean_relax<G, DENSE>(p, g, a, st, cur_id, cur_dist, cand, cand && !(sa.y >> 31), K, __hiloint2double((int)sa.w, (int)sa.z), first,
+                           future_min);
     } else {
       uint32_t lo = 0, hi = 0;
       if (s1 < lhs.len) equal_range(g, F.ilabel, rec.x, rec.z, x, lo, hi);
       for (uint32_t cb = lo; cb < hi && !st.overflow; cb += G) {
-        const bool active = cb + g.lane < hi;
-        uint4 pl = make_uint4(0, 0, 0, 0);
-        if (active) pl = __ldg(&F.payload[cb + g.lane]);
-        lean_relax<G, DENSE>(p, g, a, st, cur_id, cur_dist, active, pack_key(s1 + 1u, pl.y, 0u), 0.0 + __hiloint2double((int)pl.w, (int)pl.z),
-                             Group<G>::kBits, future_min);
+        const bool cand = cb + g.lane < hi;
+        uint4 sa = make_uint4(0, 0x80000000u, 0, 0);
+        if (cand) sa = __ldg(&F.sarc[cb + g.lane]);
+        lean_relax<G, DENSE>(p, g, a, st, cur_id, cur_dist, cand, cand && !(sa.y >> 31), lean_key(s1 + 1u, sa.y & 0x7FFFFFFFu, 0u),
+                             __hiloint2double((int)sa.w, (int)sa.z), Group<G>::kBits, future_min);
         g.sync();
       }
       for (uint32_t cb = rec.x; cb < rec.y && !st.overflow; cb += G) {
-        const bool active = cb + g.lane < rec.y;
-        uint4 pl = make_uint4(0, 0, 0, 0);
-        if (active) pl = __ldg(&F.payload[cb + g.lane]);
-        lean_relax<G, DENSE>(p, g, a, st, cur_id, cur_dist, active, pack_key(s1, pl.y, 1u), __hiloint2double((int)pl.w, (int)pl.z),
-                             Group<G>::kBits, future_min);
+        const bool cand = cb + g.lane < rec.y;
+        uint4 sa = make_uint4(0, 0x80000000u, 0, 0);
+        if (cand) sa = __ldg(&F.sarc[cb + g.lane]);
+        lean_relax<G, DENSE>(p, g, a, st, cur_id, cur_dist, cand, cand && !(sa.y >> 31), lean_key(s1, sa.y & 0x7FFFFFFFu, 1u),
+                             __hiloint2double((int)sa.w, (int)sa.z), Group<G>::kBits, future_min);
         g.sync();
       }
     }
@@ -673,7 +682,7 @@ __device__ inline LeanArena lean_arena_at(const SearchParams& p, uint32_t slot_i
 
 // Persistent batch kernel: every G-lane group pulls strings from a global queue.
 template <int G, bool DENSE>
-__global__ void __launch_bounds__(128) csp_batch_lean_kernel(SearchParams p) {
+__global__ void __launch_bounds__(128, FSTB_LEAN_MINBLOCKS) csp_batch_lean_kernel(SearchParams p) {
   extern __shared__ __align__(16) uint32_t smem_all[];
   const Group<G> g;
   const uint32_t gib = threadIdx.x / G;

@@ -15,12 +15,19 @@ constexpr uint32_t kNone = 0xFFFFFFFFu;
 //   final_w[s]   = f64 final weight (+inf = not final)
 //   ilabel[a]    = u32 search key array (binary-searched, src/fst.zig:112-136)
 //   payload[a]   = {olabel, nextstate, weight(f64 as 2xu32)} one 16-byte vector load
+//   sarc[a]      = SEARCH record of the lean batched kernel, one 16-byte load per lane per pop:
+//                  {ilabel, nextstate | dup << 31, wmin(f64 as 2xu32)}.  Arcs of one state with the
+//                  same (ilabel, nextstate) always hit the same compose tuple; the first of them in
+//                  frozen order (dup == 0) carries wmin = the smallest weight of the group and relaxes
+//                  for all of them, the others (dup == 1) only count as relax calls.  Static per
+//                  transducer, computed once at upload (see csp_lean.cuh, "fold").
 struct DevFstView {
   uint32_t num_states, num_arcs, start, max_degree;
   const uint4* state_rec;
   const double* final_w;
   const uint32_t* ilabel;
   const uint4* payload;
+  const uint4* sarc;
 };
 
 // General (non-linear) left operand as CSR in STORED arc order

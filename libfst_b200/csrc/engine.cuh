@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <map>
 #include <mutex>
+#include <unordered_map>
 #include <vector>
 
 #include "csp_kernels.cuh"
@@ -56,12 +57,14 @@ inline cudaError_t upload_fst(const HostFrozen& f, int device, DeviceFst** out) 
   const ImgState* st = f.states(); const ImgArc* ar = f.all_arcs();
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
   size_t o_rec = 0, o_fin = o_rec + al((size_t)S * 16), o_il = o_fin + al((size_t)S * 8), o_pl = o_il + al((size_t)A * 4);
-  size_t total = o_pl + al((size_t)A * 16) + 256;
+  size_t o_sa = o_pl + al((size_t)A * 16);
+  size_t total = o_sa + al((size_t)A * 16) + 256;
   std::vector<uint8_t> h(total, 0);
   uint4* rec = reinterpret_cast<uint4*>(h.data() + o_rec);
   double* fin = reinterpret_cast<double*>(h.data() + o_fin);
   uint32_t* il = reinterpret_cast<uint32_t*>(h.data() + o_il);
   uint4* pl = reinterpret_cast<uint4*>(h.data() + o_pl);
+  uint4* sa = reinterpret_cast<uint4*>(h.data() + o_sa);
   uint32_t maxdeg = 0;
   for (uint32_t s = 0; s < S; s++) {
     uint32_t b = st[s].arc_offset, e = b + st[s].num_arcs, ee = b;
@@ -77,8 +80,37 @@ inline cudaError_t upload_fst(const HostFrozen& f, int device, DeviceFst** out) 
     unsigned long long wb; std::memcpy(&wb, &ar[a].weight, 8);
     pl[a] = make_uint4(ar[a].olabel, ar[a].nextstate, (uint32_t)(wb & 0xFFFFFFFFu), (uint32_t)(wb >> 32));
   }
+  // search records: group the arcs of a state by (ilabel, nextstate); arcs are ilabel-sorted, so a group
+  // lives inside one ilabel run
+  const bool lean_ok = !f.has_negative && all_finite && S < (1u << 31);
+  if (lean_ok) {
+    std::unordered_map<uint32_t, uint32_t> first_of;   // nextstate -> first arc of the current ilabel run
+    for (uint32_t s = 0; s < S; s++) {
+      const uint32_t b = st[s].arc_offset, e = b + st[s].num_arcs;
+      uint32_t run = b;
+      while (run < e) {
+        uint32_t r2 = run;
+        while (r2 < e && ar[r2].ilabel == ar[run].ilabel) r2++;
+        first_of.clear();
+        std::vector<double> wmin;   // indexed by (leader - run)
+        wmin.assign(r2 - run, 0.0);
+        for (uint32_t a = run; a < r2; a++) {
+          auto it = first_of.find(ar[a].nextstate);
+          if (it == first_of.end()) { first_of.emplace(ar[a].nextstate, a); wmin[a - run] = ar[a].weight; }
+          else if (ar[a].weight < wmin[it->second - run]) wmin[it->second - run] = ar[a].weight;
+        }
+        for (uint32_t a = run; a < r2; a++) {
+          const uint32_t leader = first_of[ar[a].nextstate];
+          const bool dup = leader != a;
+          unsigned long long wb; std::memcpy(&wb, &wmin[leader - run], 8);
+          sa[a] = make_uint4(ar[a].ilabel, ar[a].nextstate | (dup ? 0x80000000u : 0u), (uint32_t)(wb & 0xFFFFFFFFu), (uint32_t)(wb >> 32));
+        }
+        run = r2;
+      }
+    }
+  }
   auto d = new DeviceFst();
-  d->device = device; d->bytes = total; d->serial = f.has_negative; d->lean_ok = !f.has_negative && all_finite;
+  d->device = device; d->bytes = total; d->serial = f.has_negative; d->lean_ok = lean_ok;
   cudaError_t e = cudaMalloc(&d->block, total);
   if (e != cudaSuccess) { delete d; return e; }
   e = cudaMemcpy(d->block, h.data(), total, cudaMemcpyHostToDevice);
@@ -89,6 +121,7 @@ inline cudaError_t upload_fst(const HostFrozen& f, int device, DeviceFst** out) 
   d->view.final_w = reinterpret_cast<const double*>(base + o_fin);
   d->view.ilabel = reinterpret_cast<const uint32_t*>(base + o_il);
   d->view.payload = reinterpret_cast<const uint4*>(base + o_pl);
+  d->view.sarc = reinterpret_cast<const uint4*>(base + o_sa);
   *out = d;
   return cudaSuccess;
 }
