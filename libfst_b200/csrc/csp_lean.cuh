@@ -6,7 +6,7 @@
 // first-touch order, its relax/tie rule and final pick; compose-shortest-path.zig
 // :55-61, :70-89, :91-144, :159-179) — what changes is the cost per pop:
 //
-//   * TABLE.  Either a DENSE direct-indexed table  e = ((p * S + s) * 2 + filter)
+//   * TABLE.  Either a DENSE direct-indexed table  e = (p * S + s) * 2 + filter
 //     of 16-byte records {dist, id, prev} (no hashing, no probing, neighbouring
 //     transducer states share DRAM sectors) when (len+1) * S * 2 records fit the
 //     per-string budget, or the open-addressing HASH table of 32-byte slots.
@@ -37,8 +37,12 @@
 //     the same 1024-id line on the headline workload), so a pop is one LDS +
 //     ballot, and an insert is one shared or global atomic OR — no loops.
 //   * FUTURE SET (tuples whose tentative distance is above the current level):
-//     unchanged from csp_warp.cuh — unsorted bag, turned into a radix heap over
-//     the IEEE bit pattern only when a second level is really needed.
+//     as in csp_warp.cuh — unsorted bag, turned into a radix heap over the IEEE
+//     bit pattern only when a second level is really needed.
+//   * REGISTERS.  Everything that is constant for the launch (arena offsets,
+//     capacities) is read from the kernel parameters in the constant bank at the
+//     point of use, and the cold state (radix-heap cursors, best final) lives in
+//     shared memory, so that the hot loop fits 64 registers (8 blocks per SM).
 #pragma once
 #include "csp_kernels.cuh"
 #include "csp_warp.cuh"   // kChunkIds, kNoChunk, kMaxFastTuples, bucket_of
@@ -56,6 +60,10 @@ static_assert(sizeof(DenseEnt) == 16, "DenseEnt");
 // 32-byte slot of the hash table (one DRAM sector); key all-ones = empty.  The record half is 16-byte aligned.
 struct __align__(32) LeanSlot { unsigned long long key; unsigned long long spare; double dist; uint32_t id; uint32_t prev; };
 static_assert(sizeof(LeanSlot) == 32, "LeanSlot");
+
+constexpr uint32_t kLeanColdWords = 12;   // smem words of cold per-group state (see LeanCold)
+enum LeanCold : uint32_t { kcChunkNext = 0, kcFreeHead = 1, kcOccLo = 2, kcOccHi = 3, kcHaveBest = 4, kcBestId = 5,
+                           kcBestFwLo = 6, kcBestFwHi = 7, kcBestTotLo = 8, kcBestTotHi = 9 };
 
 struct LeanLayout {
   uint64_t off_tab, off_keyof, off_l0, off_bag, off_chunks, total;
@@ -79,23 +87,10 @@ __host__ __device__ inline LeanLayout lean_layout(int G, bool dense, uint64_t ta
   L.off_bag = L.off_l0 + L.l0_bytes;
   L.off_chunks = L.off_bag + al((uint64_t)bag_cap * 4);
   L.total = (L.off_chunks + (uint64_t)chunk_cap * 128 + 255) & ~255ull;
-  L.smem_words = (128 + (uint32_t)G + L.n1 + 3) & ~3u;   // radix buckets (64 x uint2) + window + summary
+  // radix buckets (64 x uint2) + window + summary + cold state
+  L.smem_words = (128 + (uint32_t)G + L.n1 + kLeanColdWords + 3) & ~3u;
   return L;
 }
-
-struct LeanArena {
-  uint8_t* tab;                 // DenseEnt[] or LeanSlot[]
-  unsigned long long* key_of;   // id -> packed tuple key
-  uint32_t* l0;                 // ready bitmap, 32 ids per word (HBM)
-  uint32_t* bag;                // unsorted future ids; back-track scratch afterwards
-  uint32_t* chunks;             // radix-heap chunk pool
-  uint2* bucket;                // smem [64]
-  uint32_t* win;                // smem [G]   the window: line `wline` of l0
-  uint32_t* l1;                 // smem [n1]  bit per line: line has bits in HBM
-  uint64_t tab_entries;
-  uint32_t S;                   // transducer states (dense index stride)
-  uint32_t tuple_cap, chunk_cap, bag_cap, n1;
-};
 
 // Arena initialisation (layout change): table bytes 0xFF (dense: id == kNone; hash: key == empty), bitmap zero.
 __global__ void lean_arena_init_kernel(uint8_t* arena, uint64_t stride, uint32_t n_arenas, uint64_t off_l0, uint64_t tab_bytes,
@@ -109,20 +104,32 @@ __global__ void lean_arena_init_kernel(uint8_t* arena, uint64_t stride, uint32_t
   }
 }
 
+// Per-group context: two pointers.  Every other address is `base + constant-bank offset`.
+struct LeanCtx {
+  uint8_t* base;    // this group's arena in HBM
+  uint32_t* sm;     // this group's shared memory: [0,128) buckets | [128,128+G) window | l1[n1] | cold[kLeanColdWords]
+};
+template <int G> struct LgG { static constexpr int v = G == 32 ? 5 : (G == 16 ? 4 : (G == 8 ? 3 : 2)); };
+
+#define LEAN_KEYOF(p, c) (reinterpret_cast<unsigned long long*>((c).base + (p).off_keyof))
+#define LEAN_L0(p, c) (reinterpret_cast<uint32_t*>((c).base + (p).off_l0))
+#define LEAN_BAG(p, c) (reinterpret_cast<uint32_t*>((c).base + (p).off_bag))
+#define LEAN_CHUNKS(p, c) (reinterpret_cast<uint32_t*>((c).base + (p).off_chunks))
+#define LEAN_BUCKET(c) (reinterpret_cast<uint2*>((c).sm))
+#define LEAN_WIN(c) ((c).sm + 128)
+#define LEAN_L1(c, G) ((c).sm + 128 + (G))
+#define LEAN_COLD(p, c, G) ((c).sm + 128 + (G) + (p).n1)
+
+// Hot per-string state (registers).
 struct LeanState {
   uint32_t n_tuples;
-  uint32_t chunk_next, free_head, bag_len;
+  uint32_t bag_len;
   uint32_t wline;                // line held in the window, kNone = none
-  unsigned long long occupied;   // radix buckets in use
+  uint32_t relax_calls;
   unsigned long long last;       // bit pattern of the current level distance
-  unsigned long long relax_calls;
   bool low_pending;              // a ready id below the window was inserted
   bool overflow, sorted, lossy;
 };
-
-template <int G> struct LgG { static constexpr int v = G == 32 ? 5 : (G == 16 ? 4 : (G == 8 ? 3 : 2)); };
-
-__device__ __forceinline__ uint32_t ldcg_u32(const uint32_t* p) { return __ldcg(p); }
 
 // Tuple key of the lean path: high word = string position p, low word = (transducer state << 1) | filter
 // (filter is 0 or 1 for an epsilon-free left operand; states < 2^31 is checked at upload).  Packing and
@@ -134,22 +141,21 @@ __device__ __forceinline__ uint32_t lean_key_p(unsigned long long K) { return (u
 __device__ __forceinline__ uint32_t lean_key_s(unsigned long long K) { return (uint32_t)K >> 1; }
 
 // ── table access ──
-template <bool DENSE>
-__device__ __forceinline__ uint32_t lean_dense_index(const LeanArena& a, unsigned long long K) {
-  return (uint32_t)(K >> 32) * (a.S * 2u) + (uint32_t)K;
+__device__ __forceinline__ uint32_t lean_dense_index(const SearchParams& p, unsigned long long K) {
+  return (uint32_t)(K >> 32) * p.dense_stride + (uint32_t)K;
 }
 // Find the record of key K: position and contents; id == kNone <=> not present (hash: `pos` is then the
 // empty slot that ended the probe — pass it to lean_claim before storing).
 template <bool DENSE>
-__device__ __forceinline__ void lean_lookup(const LeanArena& a, unsigned long long K, uint32_t& pos, double& dist, uint32_t& id,
-                                            uint32_t& prev) {
+__device__ __forceinline__ void lean_lookup(const SearchParams& p, const LeanCtx& c, unsigned long long K, uint32_t& pos, double& dist,
+                                            uint32_t& id, uint32_t& prev) {
   if (DENSE) {
-    pos = lean_dense_index<true>(a, K);
-    const uint4 v = *reinterpret_cast<const uint4*>(a.tab + (uint64_t)pos * 16);
+    pos = lean_dense_index(p, K);
+    const uint4 v = *reinterpret_cast<const uint4*>(c.base + (uint64_t)pos * 16);
     dist = __hiloint2double((int)v.y, (int)v.x); id = v.z; prev = v.w;
   } else {
-    const LeanSlot* tab = reinterpret_cast<const LeanSlot*>(a.tab);
-    const uint32_t cap = (uint32_t)a.tab_entries;
+    const LeanSlot* tab = reinterpret_cast<const LeanSlot*>(c.base);
+    const uint32_t cap = (uint32_t)p.tab_entries;
     uint32_t i = (uint32_t)(((unsigned long long)hash_key(K) * cap) >> 32);
     for (;;) {
       const unsigned long long k = tab[i].key;
@@ -165,12 +171,12 @@ __device__ __forceinline__ void lean_lookup(const LeanArena& a, unsigned long lo
   }
 }
 // Hash table: claim a slot for the new key K, starting at the empty position the probe found (other
-// leaders of the group insert other keys concurrently).  Dense table: nothing to do.
+// lanes of the group insert other keys concurrently).  Dense table: nothing to do.
 template <bool DENSE>
-__device__ __forceinline__ uint32_t lean_claim(const LeanArena& a, unsigned long long K, uint32_t pos) {
+__device__ __forceinline__ uint32_t lean_claim(const SearchParams& p, const LeanCtx& c, unsigned long long K, uint32_t pos) {
   if (DENSE) return pos;
-  LeanSlot* tab = reinterpret_cast<LeanSlot*>(a.tab);
-  const uint32_t cap = (uint32_t)a.tab_entries;
+  LeanSlot* tab = reinterpret_cast<LeanSlot*>(c.base);
+  const uint32_t cap = (uint32_t)p.tab_entries;
   for (;;) {
     if (atomicCAS(&tab[pos].key, kEmptyKey, K) == kEmptyKey) return pos;
     if (++pos == cap) pos = 0;
@@ -179,36 +185,37 @@ __device__ __forceinline__ uint32_t lean_claim(const LeanArena& a, unsigned long
 // Write a record.  The hash variant rewrites the key half too: plain stores keep this SM's L1 copy of the
 // sector consistent with what later plain-load probes must see (the claiming CAS acts on L2 only).
 template <bool DENSE>
-__device__ __forceinline__ void lean_store(const LeanArena& a, uint32_t pos, unsigned long long K, double dist, uint32_t id, uint32_t prev) {
+__device__ __forceinline__ void lean_store(const LeanCtx& c, uint32_t pos, unsigned long long K, double dist, uint32_t id, uint32_t prev) {
   const uint4 v = make_uint4((uint32_t)__double2loint(dist), (uint32_t)__double2hiint(dist), id, prev);
   if (DENSE) {
-    *reinterpret_cast<uint4*>(a.tab + (uint64_t)pos * 16) = v;
+    *reinterpret_cast<uint4*>(c.base + (uint64_t)pos * 16) = v;
   } else {
-    uint4* sl = reinterpret_cast<uint4*>(a.tab + (uint64_t)pos * 32);
+    uint4* sl = reinterpret_cast<uint4*>(c.base + (uint64_t)pos * 32);
     sl[0] = make_uint4((uint32_t)K, (uint32_t)(K >> 32), 0u, 0u);
     sl[1] = v;
   }
 }
 template <bool DENSE>
-__device__ __forceinline__ double lean_dist_of_id(const LeanArena& a, uint32_t id) {
+__device__ __forceinline__ double lean_dist_of_id(const SearchParams& p, const LeanCtx& c, uint32_t id) {
   uint32_t pos, i2, pr; double d;
-  lean_lookup<DENSE>(a, a.key_of[id], pos, d, i2, pr);
+  lean_lookup<DENSE>(p, c, LEAN_KEYOF(p, c)[id], pos, d, i2, pr);
   return d;
 }
 
 // ── ready set ──
 // Insert ids (collective over the group; one atomic OR per inserting lane).
 template <int G>
-__device__ __forceinline__ void lean_ready_insert(const Group<G>& g, const LeanArena& a, LeanState& st, bool active, uint32_t id) {
+__device__ __forceinline__ void lean_ready_insert(const SearchParams& p, const Group<G>& g, const LeanCtx& c, LeanState& st, bool active,
+                                                  uint32_t id) {
   bool low = false;
   if (active) {
     const uint32_t line = id >> (5 + LgG<G>::v);
     const uint32_t bit = 1u << (id & 31u);
     if (line == st.wline) {
-      atomicOr(&a.win[(id >> 5) & (G - 1)], bit);
+      atomicOr(&LEAN_WIN(c)[(id >> 5) & (G - 1)], bit);
     } else {
-      atomicOr(&a.l0[id >> 5], bit);
-      atomicOr(&a.l1[line >> 5], 1u << (line & 31u));
+      atomicOr(&LEAN_L0(p, c)[id >> 5], bit);
+      atomicOr(&LEAN_L1(c, G)[line >> 5], 1u << (line & 31u));
       low = st.wline != kNone && line < st.wline;
     }
   }
@@ -217,36 +224,37 @@ __device__ __forceinline__ void lean_ready_insert(const Group<G>& g, const LeanA
 }
 // Write the window back (it holds ids above a newly inserted smaller one).
 template <int G>
-__device__ __forceinline__ void lean_window_evict(const Group<G>& g, const LeanArena& a, LeanState& st) {
+__device__ __forceinline__ void lean_window_evict(const SearchParams& p, const Group<G>& g, const LeanCtx& c, LeanState& st) {
   if (st.wline != kNone) {
-    const uint32_t w = a.win[g.lane];
-    if (w) __stcg(&a.l0[st.wline * G + g.lane], w);
-    if (g.any(w != 0)) { if (g.lane == 0) a.l1[st.wline >> 5] |= 1u << (st.wline & 31u); }
-    a.win[g.lane] = 0;
+    const uint32_t w = LEAN_WIN(c)[g.lane];
+    if (w) __stcg(&LEAN_L0(p, c)[st.wline * G + g.lane], w);
+    if (g.any(w != 0)) { if (g.lane == 0) LEAN_L1(c, G)[st.wline >> 5] |= 1u << (st.wline & 31u); }
+    LEAN_WIN(c)[g.lane] = 0;
     st.wline = kNone;
   }
   g.sync();
 }
 // Load the lowest non-empty line into the window.  False: the ready set is empty.
 template <int G>
-__device__ __forceinline__ bool lean_window_next(const Group<G>& g, const LeanArena& a, LeanState& st) {
-  const uint32_t words = min(a.n1, (st.n_tuples >> (10 + LgG<G>::v)) + 1u);
+__device__ __forceinline__ bool lean_window_next(const SearchParams& p, const Group<G>& g, const LeanCtx& c, LeanState& st) {
+  const uint32_t words = min(p.n1, (st.n_tuples >> (10 + LgG<G>::v)) + 1u);
+  uint32_t* l1 = LEAN_L1(c, G);
   for (uint32_t base = 0; base < words; base += G) {
     const uint32_t i = base + g.lane;
-    const uint32_t v = i < words ? a.l1[i] : 0u;
+    const uint32_t v = i < words ? l1[i] : 0u;
     const unsigned bal = g.ballot(v != 0);
     if (bal) {
       const int src = __ffs(bal) - 1;
       const uint32_t vv = g.shfl(v, src);
       const uint32_t line = ((base + src) << 5) + (__ffs(vv) - 1);
-      if ((int)g.lane == src) a.l1[i] = vv & (vv - 1);
+      if ((int)g.lane == src) l1[i] = vv & (vv - 1);
       st.wline = line;
-      uint32_t* wp = &a.l0[line * G + g.lane];
+      uint32_t* wp = &LEAN_L0(p, c)[line * G + g.lane];
       const uint32_t w = __ldcg(wp);
       if (w) __stcg(wp, 0u);
-      a.win[g.lane] = w;
+      LEAN_WIN(c)[g.lane] = w;
       // the keys of this line are read one pop at a time: pull them into L1 now (32*G ids * 8 B)
-      const char* kp = reinterpret_cast<const char*>(a.key_of + (uint64_t)line * 32 * G) + (size_t)g.lane * 128;
+      const char* kp = reinterpret_cast<const char*>(LEAN_KEYOF(p, c) + (uint64_t)line * 32 * G) + (size_t)g.lane * 128;
 #pragma unroll
       for (int r = 0; r < 2; r++) asm volatile("prefetch.global.L1 [%0];" ::"l"(kp + (size_t)r * G * 128));
       g.sync();
@@ -257,19 +265,53 @@ __device__ __forceinline__ bool lean_window_next(const Group<G>& g, const LeanAr
   return false;
 }
 
-// ── future set (radix heap; cold on single-level searches) ──
+// ── future set (radix heap; its cursors live in shared memory, lane 0 writes, everyone reads) ──
 template <int G>
-__device__ __forceinline__ uint32_t lean_chunk_alloc(const LeanArena& a, LeanState& st) {
-  uint32_t c;
-  if (st.free_head != kNoChunk) { c = st.free_head; st.free_head = a.chunks[(uint64_t)c * 32]; }
-  else if (st.chunk_next < a.chunk_cap) c = st.chunk_next++;
-  else { st.overflow = true; c = 0; }
-  return c;
+__device__ __forceinline__ unsigned long long lean_occupied(const SearchParams& p, const LeanCtx& c) {
+  const uint32_t* cold = LEAN_COLD(p, c, G);
+  return ((unsigned long long)cold[kcOccHi] << 32) | cold[kcOccLo];
 }
 template <int G>
-__device__ __forceinline__ void lean_bucket_push(const Group<G>& g, const LeanArena& a, LeanState& st, bool active, uint32_t id, uint32_t b) {
+__device__ __forceinline__ void lean_set_occupied(const SearchParams& p, const Group<G>& g, const LeanCtx& c, unsigned long long v) {
+  uint32_t* cold = LEAN_COLD(p, c, G);
+  if (g.lane == 0) { cold[kcOccLo] = (uint32_t)v; cold[kcOccHi] = (uint32_t)(v >> 32); }
+}
+// Take a chunk from the free list or the pool (group-uniform result).
+template <int G>
+__device__ __forceinline__ uint32_t lean_chunk_alloc(const SearchParams& p, const Group<G>& g, const LeanCtx& c, LeanState& st) {
+  uint32_t* cold = LEAN_COLD(p, c, G);
+  const uint32_t fh = cold[kcFreeHead], cn = cold[kcChunkNext];
+  uint32_t ch;
+  g.sync();
+  if (fh != kNoChunk) {
+    ch = fh;
+    const uint32_t nx = LEAN_CHUNKS(p, c)[(uint64_t)ch * 32];
+    if (g.lane == 0) cold[kcFreeHead] = nx;
+  } else if (cn < p.heap_cap) {
+    ch = cn;
+    if (g.lane == 0) cold[kcChunkNext] = cn + 1;
+  } else {
+    st.overflow = true; ch = 0;
+  }
+  g.sync();
+  return ch;
+}
+template <int G>
+__device__ __forceinline__ void lean_chunk_free(const SearchParams& p, const Group<G>& g, const LeanCtx& c, uint32_t ch) {
+  uint32_t* cold = LEAN_COLD(p, c, G);
+  const uint32_t fh = cold[kcFreeHead];
+  g.sync();
+  if (g.lane == 0) { LEAN_CHUNKS(p, c)[(uint64_t)ch * 32] = fh; cold[kcFreeHead] = ch; }
+  g.sync();
+}
+// Append ids to radix buckets (collective).  `b` in 1..64 for active lanes.
+template <int G>
+__device__ __forceinline__ void lean_bucket_push(const SearchParams& p, const Group<G>& g, const LeanCtx& c, LeanState& st, bool active,
+                                                 uint32_t id, uint32_t b) {
   unsigned m = g.ballot(active);
   const unsigned lt = g.lt_mask();
+  uint32_t* chunks = LEAN_CHUNKS(p, c);
+  unsigned long long occ = lean_occupied<G>(p, c);
   while (m) {
     const int first = __ffs(m) - 1;
     const uint32_t bb = g.shfl(b, first);
@@ -277,26 +319,28 @@ __device__ __forceinline__ void lean_bucket_push(const Group<G>& g, const LeanAr
     const unsigned same = g.ballot(mine);
     m &= ~same;
     const uint32_t k = __popc(same), rank = __popc(same & lt);
-    const bool empty = !((st.occupied >> (bb - 1)) & 1ull);
-    const uint2 hb = a.bucket[bb - 1];
+    const bool empty = !((occ >> (bb - 1)) & 1ull);
+    const uint2 hb = LEAN_BUCKET(c)[bb - 1];
     uint32_t head = empty ? kNoChunk : hb.x, cnt = empty ? kChunkIds : hb.y;
     const uint32_t space = kChunkIds - cnt;
-    if (mine && rank < space) a.chunks[(uint64_t)head * 32 + 1 + cnt + rank] = id;
+    if (mine && rank < space) chunks[(uint64_t)head * 32 + 1 + cnt + rank] = id;
     uint32_t left = k > space ? k - space : 0, done = k - left;
     if (left == 0) cnt += k;
     while (left > 0) {
-      const uint32_t c = lean_chunk_alloc<G>(a, st);
+      const uint32_t ch = lean_chunk_alloc<G>(p, g, c, st);
       if (st.overflow) return;
       const uint32_t take = left < kChunkIds ? left : kChunkIds;
-      if (g.lane == 0) a.chunks[(uint64_t)c * 32] = head;
-      if (mine && rank >= done && rank < done + take) a.chunks[(uint64_t)c * 32 + 1 + (rank - done)] = id;
-      head = c; cnt = take; done += take; left -= take;
+      if (g.lane == 0) chunks[(uint64_t)ch * 32] = head;
+      if (mine && rank >= done && rank < done + take) chunks[(uint64_t)ch * 32 + 1 + (rank - done)] = id;
+      head = ch; cnt = take; done += take; left -= take;
     }
     g.sync();
-    if (g.lane == 0) a.bucket[bb - 1] = make_uint2(head, cnt);
-    st.occupied |= 1ull << (bb - 1);
+    if (g.lane == 0) LEAN_BUCKET(c)[bb - 1] = make_uint2(head, cnt);
+    occ |= 1ull << (bb - 1);
     g.sync();
   }
+  lean_set_occupied<G>(p, g, c, occ);
+  g.sync();
 }
 template <int G>
 __device__ __forceinline__ unsigned long long lean_group_min_u64(const Group<G>& g, unsigned long long v) {
@@ -305,116 +349,121 @@ __device__ __forceinline__ unsigned long long lean_group_min_u64(const Group<G>&
   return v;
 }
 
+// Build the radix heap from the bag (or, if the bag was abandoned, from all tuples).
 template <int G, bool DENSE>
-__device__ __forceinline__ void lean_build_radix(const Group<G>& g, const LeanArena& a, LeanState& st) {
+__device__ __forceinline__ void lean_build_radix(const SearchParams& p, const Group<G>& g, const LeanCtx& c, LeanState& st) {
   st.sorted = true;
   const uint32_t n = st.lossy ? st.n_tuples : st.bag_len;
   for (uint32_t base = 0; base < n && !st.overflow; base += G) {
     const uint32_t j = base + g.lane;
     bool valid = false; uint32_t id = 0; unsigned long long k = 0;
     if (j < n) {
-      id = st.lossy ? j : a.bag[j];
-      k = (unsigned long long)__double_as_longlong(lean_dist_of_id<DENSE>(a, id));
+      id = st.lossy ? j : LEAN_BAG(p, c)[j];
+      k = (unsigned long long)__double_as_longlong(lean_dist_of_id<DENSE>(p, c, id));
       valid = k > st.last;
     }
-    if (g.any(valid)) lean_bucket_push<G>(g, a, st, valid, id, valid ? bucket_of(k, st.last) : 1u);
+    if (g.any(valid)) lean_bucket_push<G>(p, g, c, st, valid, id, valid ? bucket_of(k, st.last) : 1u);
   }
   st.bag_len = 0; st.lossy = false;
 }
 
-// Advance to the next distance level; false = the search is finished.
+// Advance to the next distance level; false = the search is finished (no valid entry left, or no
+// remaining tuple can change the result).
 template <int G, bool DENSE>
-__device__ __forceinline__ bool lean_advance_level(const SearchParams& p, const Group<G>& g, const LeanArena& a, LeanState& st,
-                                                bool have_best, double best_total, unsigned long long future_min) {
+__device__ __forceinline__ bool lean_advance_level(const SearchParams& p, const Group<G>& g, const LeanCtx& c, LeanState& st,
+                                                   unsigned long long future_min) {
+  const uint32_t* cold = LEAN_COLD(p, c, G);
+  const bool have_best = cold[kcHaveBest] != 0;
+  const double best_total = __hiloint2double((int)cold[kcBestTotHi], (int)cold[kcBestTotLo]);
   if (!st.sorted) {
     const unsigned long long fm = lean_group_min_u64<G>(g, future_min);
-    if (fm == ~0ull) return false;
+    if (fm == ~0ull) return false;   // nothing was ever pushed beyond the levels already done
+    // lower bound of every remaining distance: cannot reach or tie the best total -> done
     if (!p.exhaustive && have_best && __longlong_as_double((long long)fm) > best_total) return false;
-    lean_build_radix<G, DENSE>(g, a, st);
+    lean_build_radix<G, DENSE>(p, g, c, st);
     if (st.overflow) return false;
   }
-  while (st.occupied) {
-    const uint32_t b0 = __ffsll((long long)st.occupied);   // bucket number 1..64
-    const uint2 hb = a.bucket[b0 - 1];
+  uint32_t* chunks = LEAN_CHUNKS(p, c);
+  for (;;) {
+    unsigned long long occ = lean_occupied<G>(p, c);
+    if (occ == 0) return false;
+    const uint32_t b0 = __ffsll((long long)occ);   // bucket number 1..64
+    const uint2 hb = LEAN_BUCKET(c)[b0 - 1];
+    // pass 1: smallest valid key in the bucket
     unsigned long long m = ~0ull;
     {
-      uint32_t c = hb.x, cnt = hb.y;
-      while (c != kNoChunk) {
-        const uint32_t* ch = a.chunks + (uint64_t)c * 32;
-        const uint32_t next = ch[0];
+      uint32_t ch = hb.x, cnt = hb.y;
+      while (ch != kNoChunk) {
+        const uint32_t* cp = chunks + (uint64_t)ch * 32;
+        const uint32_t next = cp[0];
         for (uint32_t o = 0; o < cnt; o += G) {
           if (o + g.lane < cnt) {
-            const uint32_t id = ch[1 + o + g.lane];
-            const unsigned long long k = (unsigned long long)__double_as_longlong(lean_dist_of_id<DENSE>(a, id));
+            const uint32_t id = cp[1 + o + g.lane];
+            const unsigned long long k = (unsigned long long)__double_as_longlong(lean_dist_of_id<DENSE>(p, c, id));
             if (k > st.last && bucket_of(k, st.last) == b0 && k < m) m = k;
           }
         }
-        c = next; cnt = kChunkIds;
+        ch = next; cnt = kChunkIds;
       }
       m = lean_group_min_u64<G>(g, m);
     }
-    st.occupied &= ~(1ull << (b0 - 1));
+    g.sync();
+    lean_set_occupied<G>(p, g, c, occ & ~(1ull << (b0 - 1)));
     g.sync();
     if (m == ~0ull) {   // only stale entries: recycle the chunks
-      uint32_t c = hb.x;
-      while (c != kNoChunk) {
-        const uint32_t next = a.chunks[(uint64_t)c * 32];
-        g.sync();
-        if (g.lane == 0) a.chunks[(uint64_t)c * 32] = st.free_head;
-        st.free_head = c;
-        g.sync();
-        c = next;
+      uint32_t ch = hb.x;
+      while (ch != kNoChunk) {
+        const uint32_t next = chunks[(uint64_t)ch * 32];
+        lean_chunk_free<G>(p, g, c, ch);
+        ch = next;
       }
       continue;
     }
     if (!p.exhaustive && have_best && __longlong_as_double((long long)m) > best_total) return false;
+    // pass 2: redistribute relative to the new level key m
     const unsigned long long old_last = st.last;
     st.last = m;
-    uint32_t c = hb.x, cnt = hb.y;
-    while (c != kNoChunk && !st.overflow) {
-      const uint32_t* ch = a.chunks + (uint64_t)c * 32;
-      const uint32_t next = ch[0];
+    uint32_t ch = hb.x, cnt = hb.y;
+    while (ch != kNoChunk && !st.overflow) {
+      const uint32_t* cp = chunks + (uint64_t)ch * 32;
+      const uint32_t next = cp[0];
       for (uint32_t o = 0; o < cnt && !st.overflow; o += G) {
         bool valid = false; uint32_t id = 0; unsigned long long k = 0;
         if (o + g.lane < cnt) {
-          id = ch[1 + o + g.lane];
-          k = (unsigned long long)__double_as_longlong(lean_dist_of_id<DENSE>(a, id));
+          id = cp[1 + o + g.lane];
+          k = (unsigned long long)__double_as_longlong(lean_dist_of_id<DENSE>(p, c, id));
           valid = k > old_last && bucket_of(k, old_last) == b0;
         }
-        lean_ready_insert<G>(g, a, st, valid && k == m, id);
+        lean_ready_insert<G>(p, g, c, st, valid && k == m, id);
         const bool tb = valid && k != m;
-        if (g.any(tb)) lean_bucket_push<G>(g, a, st, tb, id, tb ? bucket_of(k, m) : 1u);
+        if (g.any(tb)) lean_bucket_push<G>(p, g, c, st, tb, id, tb ? bucket_of(k, m) : 1u);
       }
-      g.sync();
-      if (g.lane == 0) a.chunks[(uint64_t)c * 32] = st.free_head;   // recycle
-      st.free_head = c;
-      g.sync();
-      c = next; cnt = kChunkIds;
+      lean_chunk_free<G>(p, g, c, ch);   // recycle
+      ch = next; cnt = kChunkIds;
     }
     return !st.overflow;
   }
-  return false;
 }
 
 // ── one relaxation per lane ──
 // `active` lanes hold DISTINCT targets (the static search records fold parallel arcs, see
-// device_types.cuh `sarc`); `cand` lanes are all arcs of the expansion (the reference's relax calls).
+// device_types.cuh `sarc`); `n_cand` = all arcs of the expansion (the reference's relax calls).
 // `first`: lanes that precede the other lanes in the reference's expansion order (match arcs
 // :182-202 before input-epsilon arcs :254-278); only used to number newly discovered tuples.
 template <int G, bool DENSE>
-__device__ __forceinline__ void lean_relax(const SearchParams& p, const Group<G>& g, const LeanArena& a, LeanState& st, uint32_t cur_id,
-                                           double cur_dist, bool cand, bool active, unsigned long long K, double wmin, unsigned first,
+__device__ __forceinline__ void lean_relax(const SearchParams& p, const Group<G>& g, const LeanCtx& c, LeanState& st, uint32_t cur_id,
+                                           uint32_t n_cand, bool active, unsigned long long K, double wmin, unsigned first,
                                            unsigned long long& future_min) {
-  const unsigned cm = g.ballot(cand);
-  if (cm == 0) return;
-  st.relax_calls += __popc(cm);
+  if (n_cand == 0) return;
+  st.relax_calls += n_cand;
   uint32_t pos = 0, old_id = 0, old_prev = kNone; double old_dist = d_inf();
-  if (active) lean_lookup<DENSE>(a, K, pos, old_dist, old_id, old_prev);
-  const double nd = cur_dist + wmin;   // smallest new distance over the parallel arcs (fl(c + w) is monotone in w)
+  if (active) lean_lookup<DENSE>(p, c, K, pos, old_dist, old_id, old_prev);
+  // smallest new distance over the parallel arcs (fl(c + w) is monotone in w)
+  const double nd = __longlong_as_double((long long)st.last) + wmin;
   const bool is_new = active && old_id == kNone;
   const unsigned newmask = g.ballot(is_new);
   const uint32_t n_new = __popc(newmask);
-  if (st.n_tuples + n_new > a.tuple_cap) { st.overflow = true; return; }
+  if (st.n_tuples + n_new > p.tuple_cap) { st.overflow = true; return; }
   bool lowered = false;
   uint32_t my_id = old_id;
   if (active) {
@@ -423,28 +472,28 @@ __device__ __forceinline__ void lean_relax(const SearchParams& p, const Group<G>
       const bool in_first = (first >> g.lane) & 1u;
       const uint32_t rank = in_first ? __popc(newmask & first & lt) : (__popc(newmask & first) + __popc(newmask & ~first & lt));
       my_id = st.n_tuples + rank;   // discovery order == reference expansion order (:80-87)
-      a.key_of[my_id] = K;
-      pos = lean_claim<DENSE>(a, K, pos);
+      LEAN_KEYOF(p, c)[my_id] = K;
+      pos = lean_claim<DENSE>(p, c, K, pos);
     }
     lowered = is_new || nd < old_dist;                                                         // :109-114, :137-142
     const bool take = lowered || (nd == old_dist && (old_prev == kNone || cur_id < old_prev)); // :115-126
-    if (take) lean_store<DENSE>(a, pos, K, nd, my_id, cur_id);
+    if (take) lean_store<DENSE>(c, pos, K, nd, my_id, cur_id);
   }
   st.n_tuples += n_new;
   // queue: ready set if at the current level, else future set
   const unsigned long long k = (unsigned long long)__double_as_longlong(nd);
   const bool to_ready = lowered && k == st.last;
   const bool to_future = lowered && k != st.last;
-  lean_ready_insert<G>(g, a, st, to_ready, my_id);
+  lean_ready_insert<G>(p, g, c, st, to_ready, my_id);
   const unsigned f = g.ballot(to_future);
   if (f) {
     if (to_future && k < future_min) future_min = k;
     if (st.sorted) {
-      lean_bucket_push<G>(g, a, st, to_future, my_id, to_future ? bucket_of(k, st.last) : 1u);
+      lean_bucket_push<G>(p, g, c, st, to_future, my_id, to_future ? bucket_of(k, st.last) : 1u);
     } else if (!st.lossy) {
       const uint32_t cnt = __popc(f);
-      if (st.bag_len + cnt <= a.bag_cap) {
-        if (to_future) a.bag[st.bag_len + __popc(f & g.lt_mask())] = my_id;
+      if (st.bag_len + cnt <= p.bag_cap) {
+        if (to_future) LEAN_BAG(p, c)[st.bag_len + __popc(f & g.lt_mask())] = my_id;
         st.bag_len += cnt;
       } else {
         st.lossy = true;   // bag abandoned; a rescan of all tuples rebuilds the future set if ever needed
@@ -481,52 +530,52 @@ __device__ inline bool lean_recover_arc(const DevFstView& F, const LhsBytes& lhs
 }
 
 template <int G, bool DENSE>
-__device__ inline int32_t search_lean(const SearchParams& p, const LhsBytes& lhs, const LeanArena& a, uint32_t* out_path_len,
-                                      uint64_t* out_pool_off, double* out_final_w, uint32_t* out_n_tuples,
-                                      unsigned long long* out_relax) {
+__device__ __forceinline__ int32_t search_lean(const SearchParams& p, const LhsBytes& lhs, const LeanCtx& c, uint32_t* out_path_len,
+                                               uint64_t* out_pool_off, double* out_final_w, uint32_t* out_n_tuples,
+                                               unsigned long long* out_relax) {
   const Group<G> g;
   LeanState st;
-  st.n_tuples = 0; st.chunk_next = 0; st.free_head = kNoChunk; st.bag_len = 0; st.wline = 0; st.occupied = 0; st.last = 0;
-  st.relax_calls = 0; st.low_pending = false; st.overflow = false; st.sorted = false; st.lossy = false;
+  st.n_tuples = 0; st.bag_len = 0; st.wline = 0; st.relax_calls = 0; st.last = 0;
+  st.low_pending = false; st.overflow = false; st.sorted = false; st.lossy = false;
   unsigned long long future_min = ~0ull;
+  unsigned long long relax_hi = 0;   // relax calls beyond 31 bits (flushed rarely)
   *out_path_len = 0; *out_pool_off = 0; *out_final_w = d_inf(); *out_n_tuples = 0; *out_relax = 0;
   const DevFstView& F = p.fst;
   if (F.start == kNone) return kStNoPath;
+  unsigned long long* key_of = LEAN_KEYOF(p, c);
+  uint32_t* cold = LEAN_COLD(p, c, G);
 
   // initial tuple: id 0, dist One, ready at level 0 (compose-shortest-path.zig:146-153)
   if (g.lane == 0) {
     const unsigned long long k0 = lean_key(0, F.start, 0);
     uint32_t pos, id, prev; double d;
-    lean_lookup<DENSE>(a, k0, pos, d, id, prev);
-    pos = lean_claim<DENSE>(a, k0, pos);
-    lean_store<DENSE>(a, pos, k0, 0.0, 0u, kNone);
-    a.key_of[0] = k0;
+    lean_lookup<DENSE>(p, c, k0, pos, d, id, prev);
+    pos = lean_claim<DENSE>(p, c, k0, pos);
+    lean_store<DENSE>(c, pos, k0, 0.0, 0u, kNone);
+    key_of[0] = k0;
+    cold[kcChunkNext] = 0; cold[kcFreeHead] = kNoChunk; cold[kcOccLo] = 0; cold[kcOccHi] = 0; cold[kcHaveBest] = 0;
   }
-  a.win[g.lane] = g.lane == 0 ? 1u : 0u;   // window = line 0 (all of l0 is zero between strings)
+  LEAN_WIN(c)[g.lane] = g.lane == 0 ? 1u : 0u;   // window = line 0 (all of l0 is zero between strings)
   st.n_tuples = 1;
   g.sync();
-
-  bool have_best = false; uint32_t best_id = 0; double best_fw = d_inf(), best_total = d_inf();
-  double cur_dist = 0.0;
 
   for (;;) {
     if (st.overflow) break;
     // ── pop the smallest ready id (:159-163; the set only holds unsettled tuples at the level distance) ──
-    if (st.low_pending) { lean_window_evict<G>(g, a, st); st.low_pending = false; }
-    const uint32_t w = a.win[g.lane];
+    if (st.low_pending) { lean_window_evict<G>(p, g, c, st); st.low_pending = false; }
+    const uint32_t w = LEAN_WIN(c)[g.lane];
     const unsigned bal = g.ballot(w != 0);
     if (bal == 0) {
-      if (lean_window_next<G>(g, a, st)) continue;
-      if (!lean_advance_level<G, DENSE>(p, g, a, st, have_best, best_total, future_min)) break;
-      cur_dist = __longlong_as_double((long long)st.last);
+      if (lean_window_next<G>(p, g, c, st)) continue;
+      if (!lean_advance_level<G, DENSE>(p, g, c, st, future_min)) break;
       continue;
     }
     const int src = __ffs(bal) - 1;
     const uint32_t ww = g.shfl(w, src);
     const uint32_t cur_id = ((st.wline * G + src) << 5) + (__ffs(ww) - 1);
-    if ((int)g.lane == src) a.win[src] = ww & (ww - 1);
+    if ((int)g.lane == src) LEAN_WIN(c)[src] = ww & (ww - 1);
     g.sync();
-    const unsigned long long ckey = a.key_of[cur_id];
+    const unsigned long long ckey = key_of[cur_id];
     const uint32_t s1 = lean_key_p(ckey), s2 = lean_key_s(ckey);
 
     // final check (:165-179): only the last state of the string acceptor is final, weight One
@@ -534,10 +583,19 @@ __device__ inline int32_t search_lean(const SearchParams& p, const LhsBytes& lhs
       const double fw2 = F.final_w[s2];
       if (!d_isinf(fw2)) {
         const double final_w = 0.0 + fw2;
-        const double total = cur_dist + final_w;
+        const double total = __longlong_as_double((long long)st.last) + final_w;
+        const bool have_best = cold[kcHaveBest] != 0;
+        const double best_total = __hiloint2double((int)cold[kcBestTotHi], (int)cold[kcBestTotLo]);
+        const uint32_t best_id = cold[kcBestId];
+        g.sync();
         if (!have_best || total < best_total || (total == best_total && cur_id < best_id)) {
-          have_best = true; best_id = cur_id; best_fw = final_w; best_total = total;
+          if (g.lane == 0) {
+            cold[kcHaveBest] = 1; cold[kcBestId] = cur_id;
+            cold[kcBestFwLo] = (uint32_t)__double2loint(final_w); cold[kcBestFwHi] = (uint32_t)__double2hiint(final_w);
+            cold[kcBestTotLo] = (uint32_t)__double2loint(total); cold[kcBestTotHi] = (uint32_t)__double2hiint(total);
+          }
         }
+        g.sync();
       }
     }
     // ── expansion (:182-202 match arcs, then :254-278 input-epsilon arcs; filter is 0 or 1 here) ──
@@ -547,17 +605,15 @@ __device__ inline int32_t search_lean(const SearchParams& p, const LhsBytes& lhs
     if (deg <= (uint32_t)G) {
       // one lane per arc of the state, in frozen order (epsilon prefix first)
       const uint32_t arc = rec.x + g.lane;
-      const bool valid = g.lane < deg;
       uint4 sa = make_uint4(0xFFFFFFFFu, 0x80000000u, 0, 0);
-      if (valid) sa = __ldg(&F.sarc[arc]);
-      const bool is_match = sa.x == x;               // invalid lanes hold ilabel 0xFFFFFFFF, x is never that
-      const bool is_eps = valid && arc < rec.y;
-      const bool cand = is_match || is_eps;
+      if (g.lane < deg) sa = __ldg(&F.sarc[arc]);
+      const bool is_match = sa.x == x;               // idle lanes hold ilabel 0xFFFFFFFF, x is never that
+      const bool is_eps = arc < rec.y;               // the epsilon prefix [arc_begin, eps_end)
       const uint32_t nxt = sa.y & 0x7FFFFFFFu;
       const unsigned long long K = is_match ? lean_key(s1 + 1u, nxt, 0u) : lean_key(s1, nxt, 1u);
       const unsigned first = g.ballot(is_match);
-      lean_relax<G, DENSE>(p, g, a, st, cur_id, cur_dist, cand, cand && !(sa.y >> 31), K, __hiloint2double((int)sa.w, (int)sa.z), first,
-                           future_min);
+      lean_relax<G, DENSE>(p, g, c, st, cur_id, __popc(first) + (rec.y - rec.x), (is_match || is_eps) && !(sa.y >> 31), K,
+                           __hiloint2double((int)sa.w, (int)sa.z), first, future_min);
     } else {
       uint32_t lo = 0, hi = 0;
       if (s1 < lhs.len) equal_range(g, F.ilabel, rec.x, rec.z, x, lo, hi);
@@ -565,7 +621,7 @@ __device__ inline int32_t search_lean(const SearchParams& p, const LhsBytes& lhs
         const bool cand = cb + g.lane < hi;
         uint4 sa = make_uint4(0, 0x80000000u, 0, 0);
         if (cand) sa = __ldg(&F.sarc[cb + g.lane]);
-        lean_relax<G, DENSE>(p, g, a, st, cur_id, cur_dist, cand, cand && !(sa.y >> 31), lean_key(s1 + 1u, sa.y & 0x7FFFFFFFu, 0u),
+        lean_relax<G, DENSE>(p, g, c, st, cur_id, min(hi - cb, (uint32_t)G), cand && !(sa.y >> 31), lean_key(s1 + 1u, sa.y & 0x7FFFFFFFu, 0u),
                              __hiloint2double((int)sa.w, (int)sa.z), Group<G>::kBits, future_min);
         g.sync();
       }
@@ -573,17 +629,22 @@ __device__ inline int32_t search_lean(const SearchParams& p, const LhsBytes& lhs
         const bool cand = cb + g.lane < rec.y;
         uint4 sa = make_uint4(0, 0x80000000u, 0, 0);
         if (cand) sa = __ldg(&F.sarc[cb + g.lane]);
-        lean_relax<G, DENSE>(p, g, a, st, cur_id, cur_dist, cand, cand && !(sa.y >> 31), lean_key(s1, sa.y & 0x7FFFFFFFu, 1u),
+        lean_relax<G, DENSE>(p, g, c, st, cur_id, min(rec.y - cb, (uint32_t)G), cand && !(sa.y >> 31), lean_key(s1, sa.y & 0x7FFFFFFFu, 1u),
                              __hiloint2double((int)sa.w, (int)sa.z), Group<G>::kBits, future_min);
         g.sync();
       }
     }
+    if (st.relax_calls >= 0x80000000u) { relax_hi += st.relax_calls; st.relax_calls = 0; }
   }
 
   int32_t status = kStPath;
   uint32_t plen = 0;
   unsigned long long poff = 0;
-  uint32_t* scratch = a.bag;   // the future set is dead now; bag_cap >= tuple_cap by construction
+  uint32_t* scratch = LEAN_BAG(p, c);   // the future set is dead now; bag_cap >= tuple_cap by construction
+  g.sync();
+  const bool have_best = cold[kcHaveBest] != 0;
+  const uint32_t best_id = cold[kcBestId];
+  const double best_fw = __hiloint2double((int)cold[kcBestFwHi], (int)cold[kcBestFwLo]);
   if (st.overflow) {
     status = kStRetry;
   } else if (!have_best) {
@@ -593,7 +654,7 @@ __device__ inline int32_t search_lean(const SearchParams& p, const LhsBytes& lhs
       uint32_t cur = best_id;
       while (cur != 0) {
         uint32_t pos, id, prev; double d;
-        lean_lookup<DENSE>(a, a.key_of[cur], pos, d, id, prev);
+        lean_lookup<DENSE>(p, c, key_of[cur], pos, d, id, prev);
         if (prev == kNone) { status = kStNoPath; break; }             // :375-377
         if (plen >= st.n_tuples) { status = kStCycle; break; }        // hazard H1 (reference: out of memory)
         scratch[plen++] = cur;
@@ -609,11 +670,11 @@ __device__ inline int32_t search_lean(const SearchParams& p, const LhsBytes& lhs
     if (status == kStPath) {
       bool bad = false;
       for (uint32_t i = g.lane; i < plen; i += G) {
-        const unsigned long long Kv = a.key_of[scratch[i]];
+        const unsigned long long Kv = key_of[scratch[i]];
         uint32_t pos, id, prev, id2, prev2; double dv, du;
-        lean_lookup<DENSE>(a, Kv, pos, dv, id, prev);
-        const unsigned long long Ku = a.key_of[prev];
-        lean_lookup<DENSE>(a, Ku, pos, du, id2, prev2);
+        lean_lookup<DENSE>(p, c, Kv, pos, dv, id, prev);
+        const unsigned long long Ku = key_of[prev];
+        lean_lookup<DENSE>(p, c, Ku, pos, du, id2, prev2);
         PoolArc pa; pa.ilabel = 0; pa.olabel = 0; pa.weight = 0.0;
         if (!lean_recover_arc(F, lhs, Ku, Kv, du, dv, pa)) bad = true;
         p.pool[poff + i] = pa;
@@ -627,68 +688,51 @@ __device__ inline int32_t search_lean(const SearchParams& p, const LhsBytes& lhs
   g.sync();
   const uint32_t n = st.n_tuples;
   if (DENSE) {
-    if ((uint64_t)n * 4 < a.tab_entries) {
+    if ((uint64_t)n * 4 < p.tab_entries) {
       for (uint32_t i = g.lane; i < n; i += G)
-        *reinterpret_cast<uint4*>(a.tab + (uint64_t)lean_dense_index<true>(a, a.key_of[i]) * 16) = make_uint4(~0u, ~0u, ~0u, ~0u);
+        *reinterpret_cast<uint4*>(c.base + (uint64_t)lean_dense_index(p, key_of[i]) * 16) = make_uint4(~0u, ~0u, ~0u, ~0u);
     } else {
-      uint4* t = reinterpret_cast<uint4*>(a.tab);
-      for (uint64_t i = g.lane; i < a.tab_entries; i += G) t[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+      uint4* t = reinterpret_cast<uint4*>(c.base);
+      for (uint64_t i = g.lane; i < p.tab_entries; i += G) t[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
     }
   } else {
     // two phases: resolve every tuple's slot first (probing needs intact chains), then clear
-    uint32_t* slot_tmp = reinterpret_cast<uint32_t*>(a.key_of);
+    uint32_t* slot_tmp = reinterpret_cast<uint32_t*>(key_of);
     for (uint32_t base = 0; base < n; base += G) {
       const uint32_t i = base + g.lane;
       uint32_t sl = 0, id, prev; double d;
-      if (i < n) lean_lookup<false>(a, a.key_of[i], sl, d, id, prev);
+      if (i < n) lean_lookup<false>(p, c, key_of[i], sl, d, id, prev);
       g.sync();                        // all keys of this stripe are read before any is overwritten
       if (i < n) slot_tmp[i] = sl;     // aliases key_of[i/2]: only stripes already resolved
       g.sync();
     }
-    LeanSlot* tab = reinterpret_cast<LeanSlot*>(a.tab);
+    LeanSlot* tab = reinterpret_cast<LeanSlot*>(c.base);
     for (uint32_t i = g.lane; i < n; i += G) tab[slot_tmp[i]].key = kEmptyKey;
   }
   if (st.overflow) {
     // aborted searches can leave ready bits behind
-    for (uint32_t i = g.lane; i < ((n + 32u * G - 1) / (32u * G)) * G; i += G) a.l0[i] = 0;
-    for (uint32_t i = g.lane; i < a.n1; i += G) a.l1[i] = 0;
-    a.win[g.lane] = 0;
+    for (uint32_t i = g.lane; i < ((n + 32u * G - 1) / (32u * G)) * G; i += G) LEAN_L0(p, c)[i] = 0;
+    for (uint32_t i = g.lane; i < p.n1; i += G) LEAN_L1(c, G)[i] = 0;
+    LEAN_WIN(c)[g.lane] = 0;
   }
   g.sync();
   *out_path_len = plen; *out_pool_off = poff; *out_final_w = (status == kStPath) ? best_fw : d_inf();
-  *out_n_tuples = st.n_tuples; *out_relax = st.relax_calls;
+  *out_n_tuples = st.n_tuples; *out_relax = relax_hi + st.relax_calls;
   return status;
-}
-
-template <int G>
-__device__ inline LeanArena lean_arena_at(const SearchParams& p, uint32_t slot_idx, uint32_t* smem_grp) {
-  const LeanLayout L = lean_layout(G, p.dense != 0, p.tab_entries, p.tuple_cap, p.heap_cap, p.bag_cap);
-  uint8_t* base = p.arena + (uint64_t)slot_idx * p.arena_stride;
-  LeanArena a;
-  a.tab = base + L.off_tab;
-  a.key_of = reinterpret_cast<unsigned long long*>(base + L.off_keyof);
-  a.l0 = reinterpret_cast<uint32_t*>(base + L.off_l0);
-  a.bag = reinterpret_cast<uint32_t*>(base + L.off_bag);
-  a.chunks = reinterpret_cast<uint32_t*>(base + L.off_chunks);
-  a.bucket = reinterpret_cast<uint2*>(smem_grp);
-  a.win = smem_grp + 128; a.l1 = a.win + G;
-  a.tab_entries = p.tab_entries; a.S = p.fst.num_states;
-  a.tuple_cap = p.tuple_cap; a.chunk_cap = p.heap_cap; a.bag_cap = p.bag_cap; a.n1 = L.n1;
-  const unsigned lane = (threadIdx.x & 31u) % G;
-  for (uint32_t i = lane; i < L.smem_words - 128; i += G) a.win[i] = 0;
-  __syncwarp();
-  return a;
 }
 
 // Persistent batch kernel: every G-lane group pulls strings from a global queue.
 template <int G, bool DENSE>
-__global__ void __launch_bounds__(128, FSTB_LEAN_MINBLOCKS) csp_batch_lean_kernel(SearchParams p) {
+__global__ void __launch_bounds__(128, FSTB_LEAN_MINBLOCKS) csp_batch_lean_kernel(const __grid_constant__ SearchParams p) {
   extern __shared__ __align__(16) uint32_t smem_all[];
   const Group<G> g;
   const uint32_t gib = threadIdx.x / G;
   const uint32_t gslot = blockIdx.x * (blockDim.x / G) + gib;
-  const LeanLayout L = lean_layout(G, DENSE, p.tab_entries, p.tuple_cap, p.heap_cap, p.bag_cap);
-  const LeanArena a = lean_arena_at<G>(p, gslot, smem_all + (size_t)gib * L.smem_words);
+  LeanCtx c;
+  c.base = p.arena + (uint64_t)gslot * p.arena_stride;
+  c.sm = smem_all + (size_t)gib * p.smem_words;
+  for (uint32_t i = 128 + g.lane; i < p.smem_words; i += G) c.sm[i] = 0;   // window, summary and cold state start empty
+  g.sync();
   unsigned long long relax_total = 0, tuple_total = 0;
   for (;;) {
     uint32_t item = 0;
@@ -698,7 +742,7 @@ __global__ void __launch_bounds__(128, FSTB_LEAN_MINBLOCKS) csp_batch_lean_kerne
     const uint32_t idx = p.order ? p.order[item] : item;
     LhsBytes lhs; lhs.s = p.bytes + p.offsets[idx]; lhs.len = (uint32_t)(p.offsets[idx + 1] - p.offsets[idx]);
     uint32_t plen; uint64_t poff; double fw; uint32_t nt; unsigned long long nr;
-    const int32_t status = search_lean<G, DENSE>(p, lhs, a, &plen, &poff, &fw, &nt, &nr);
+    const int32_t status = search_lean<G, DENSE>(p, lhs, c, &plen, &poff, &fw, &nt, &nr);
     if (g.lane == 0) {
       p.status[idx] = status; p.path_len[idx] = plen; p.pool_off[idx] = poff; p.final_w[idx] = fw; p.n_tuples[idx] = nt;
     }

@@ -83,6 +83,11 @@ struct SearchParams {
   uint32_t exhaustive;
   uint32_t dense;          // lean path: 1 = direct-indexed table, 0 = hash table
   uint64_t tab_entries;    // lean path: dense records ((max_len+1) * S * 2) or hash slots
+  // lean path: arena geometry precomputed on the host (read from the constant bank at the point of use)
+  uint64_t off_keyof, off_l0, off_bag, off_chunks;
+  uint32_t n1;             // ready-bitmap summary words
+  uint32_t smem_words;     // shared-memory words per group
+  uint32_t dense_stride;   // 2 * S: dense index = p * dense_stride + ((s << 1) | filter)
   // work queue + counters
   uint32_t* queue_head;
   unsigned long long* pool_cursor;

@@ -249,6 +249,11 @@ class Engine {
       p.arena = static_cast<uint8_t*>(d_workspace_); p.arena_stride = gm.stride;
       p.hash_cap = gm.hash_cap; p.tuple_cap = gm.tuple_cap; p.heap_cap = gm.heap_cap; p.bag_cap = gm.bag_cap; p.exhaustive = cfg.exhaustive;
       p.dense = gm.dense ? 1u : 0u; p.tab_entries = gm.tab_entries;
+      if (gm.kind == kLean) {
+        const LeanLayout L = lean_layout((int)gm.G, gm.dense, gm.tab_entries, gm.tuple_cap, gm.heap_cap, gm.bag_cap);
+        p.off_keyof = L.off_keyof; p.off_l0 = L.off_l0; p.off_bag = L.off_bag; p.off_chunks = L.off_chunks;
+        p.n1 = L.n1; p.smem_words = L.smem_words; p.dense_stride = fst->view.num_states * 2u;
+      }
       p.queue_head = d_cnt + 0;
       p.pool_cursor = reinterpret_cast<unsigned long long*>(d_cnt + 2);
       p.relax_counter = reinterpret_cast<unsigned long long*>(d_cnt + 4);
