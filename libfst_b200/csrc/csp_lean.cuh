@@ -37,8 +37,15 @@
 //     the same 1024-id line on the headline workload), so a pop is one LDS +
 //     ballot, and an insert is one shared or global atomic OR — no loops.
 //   * FUTURE SET (tuples whose tentative distance is above the current level):
-//     as in csp_warp.cuh — unsorted bag, turned into a radix heap over the IEEE
-//     bit pattern only when a second level is really needed.
+//     nothing is recorded while the first level runs (only the smallest pushed
+//     distance, for the early stop).  If a second level is really needed, one
+//     scan over all tuples builds a radix heap over the IEEE bit pattern of the
+//     distances (64 buckets by the highest differing bit; entries are ids,
+//     validated against the tuple's current distance when visited).
+//   * LOCKSTEP GROUPS.  The kernel is one loop whose iteration is "one step of
+//     my string" (fetch / one pop / finish) with a warp-wide reconvergence at the
+//     top, so two 16-lane groups in a warp issue their pops together instead of
+//     drifting into different loops.
 //   * REGISTERS.  Everything that is constant for the launch (arena offsets,
 //     capacities) is read from the kernel parameters in the constant bank at the
 //     point of use, and the cold state (radix-heap cursors, best final) lives in
@@ -66,14 +73,13 @@ enum LeanCold : uint32_t { kcChunkNext = 0, kcFreeHead = 1, kcOccLo = 2, kcOccHi
                            kcBestFwLo = 6, kcBestFwHi = 7, kcBestTotLo = 8, kcBestTotHi = 9 };
 
 struct LeanLayout {
-  uint64_t off_tab, off_keyof, off_l0, off_bag, off_chunks, total;
+  uint64_t off_tab, off_keyof, off_l0, off_chunks, total;
   uint64_t tab_bytes, l0_bytes;
   uint32_t n1;           // summary words (one bit per window line)
   uint32_t smem_words;   // u32 words of shared memory per group
 };
 // `tab_entries`: dense = (max_len + 1) * S * 2 records of 16 B; hash = slots of 32 B.
-__host__ __device__ inline LeanLayout lean_layout(int G, bool dense, uint64_t tab_entries, uint32_t tuple_cap, uint32_t chunk_cap,
-                                                  uint32_t bag_cap) {
+__host__ __device__ inline LeanLayout lean_layout(int G, bool dense, uint64_t tab_entries, uint32_t tuple_cap, uint32_t chunk_cap) {
   LeanLayout L;
   auto al = [](uint64_t x) { return (x + 127) & ~127ull; };
   const uint32_t ids_per_line = 32u * (uint32_t)G;
@@ -83,9 +89,8 @@ __host__ __device__ inline LeanLayout lean_layout(int G, bool dense, uint64_t ta
   L.l0_bytes = al((uint64_t)lines * G * 4);
   L.off_tab = 0;
   L.off_keyof = L.tab_bytes;
-  L.off_l0 = L.off_keyof + al((uint64_t)tuple_cap * 8);
-  L.off_bag = L.off_l0 + L.l0_bytes;
-  L.off_chunks = L.off_bag + al((uint64_t)bag_cap * 4);
+  L.off_l0 = L.off_keyof + al((uint64_t)tuple_cap * (dense ? 4 : 8));   // id -> compact key (dense) / 64-bit key (hash)
+  L.off_chunks = L.off_l0 + L.l0_bytes;
   L.total = (L.off_chunks + (uint64_t)chunk_cap * 128 + 255) & ~255ull;
   // radix buckets (64 x uint2) + window + summary + cold state
   L.smem_words = (128 + (uint32_t)G + L.n1 + kLeanColdWords + 3) & ~3u;
@@ -111,9 +116,8 @@ struct LeanCtx {
 };
 template <int G> struct LgG { static constexpr int v = G == 32 ? 5 : (G == 16 ? 4 : (G == 8 ? 3 : 2)); };
 
-#define LEAN_KEYOF(p, c) (reinterpret_cast<unsigned long long*>((c).base + (p).off_keyof))
+#define LEAN_KEYOF(p, c) ((c).base + (p).off_keyof)
 #define LEAN_L0(p, c) (reinterpret_cast<uint32_t*>((c).base + (p).off_l0))
-#define LEAN_BAG(p, c) (reinterpret_cast<uint32_t*>((c).base + (p).off_bag))
 #define LEAN_CHUNKS(p, c) (reinterpret_cast<uint32_t*>((c).base + (p).off_chunks))
 #define LEAN_BUCKET(c) (reinterpret_cast<uint2*>((c).sm))
 #define LEAN_WIN(c) ((c).sm + 128)
@@ -123,37 +127,53 @@ template <int G> struct LgG { static constexpr int v = G == 32 ? 5 : (G == 16 ? 
 // Hot per-string state (registers).
 struct LeanState {
   uint32_t n_tuples;
-  uint32_t bag_len;
   uint32_t wline;                // line held in the window, kNone = none
   uint32_t relax_calls;
   unsigned long long last;       // bit pattern of the current level distance
+  unsigned long long future_min; // per lane: smallest distance pushed beyond the current level
+  unsigned long long relax_hi;   // relax calls beyond 31 bits (flushed rarely)
   bool low_pending;              // a ready id below the window was inserted
-  bool overflow, sorted, lossy;
+  bool overflow;                 // tuple capacity exhausted -> retry with a larger arena
+  bool heap_overflow;            // radix-heap pool exhausted -> retry with a deeper pool
+  bool sorted;                   // the radix heap exists (a second level was needed)
 };
 
-// Tuple key of the lean path: high word = string position p, low word = (transducer state << 1) | filter
-// (filter is 0 or 1 for an epsilon-free left operand; states < 2^31 is checked at upload).  Packing and
-// unpacking are register moves.
-__device__ __forceinline__ unsigned long long lean_key(uint32_t p, uint32_t s, uint32_t f) {
-  return ((unsigned long long)p << 32) | (unsigned long long)((s << 1) | f);
+// Tuple key of the lean path as a (P, SF) pair: P = string position, SF = (transducer state << 1) | filter
+// (filter is 0 or 1 for an epsilon-free left operand; states < 2^31 is checked at upload).
+//   hash table:  64-bit key (P << 32) | SF.
+//   dense table: index P * dense_stride + SF; id -> key array holds the COMPACT 32-bit form
+//                (P << key_sbits) | SF  (fits: the dense table has < 2^30 records).
+template <bool DENSE> struct LeanKeyT { using type = unsigned long long; };
+template <> struct LeanKeyT<true> { using type = uint32_t; };
+
+template <bool DENSE>
+__device__ __forceinline__ void lean_keyof_store(const SearchParams& p, const LeanCtx& c, uint32_t id, uint32_t P, uint32_t SF) {
+  if (DENSE) reinterpret_cast<uint32_t*>(LEAN_KEYOF(p, c))[id] = (P << p.key_sbits) | SF;
+  else reinterpret_cast<unsigned long long*>(LEAN_KEYOF(p, c))[id] = ((unsigned long long)P << 32) | SF;
 }
-__device__ __forceinline__ uint32_t lean_key_p(unsigned long long K) { return (uint32_t)(K >> 32); }
-__device__ __forceinline__ uint32_t lean_key_s(unsigned long long K) { return (uint32_t)K >> 1; }
+template <bool DENSE>
+__device__ __forceinline__ void lean_keyof_load(const SearchParams& p, const LeanCtx& c, uint32_t id, uint32_t& P, uint32_t& SF) {
+  if (DENSE) {
+    const uint32_t k = reinterpret_cast<const uint32_t*>(LEAN_KEYOF(p, c))[id];
+    P = k >> p.key_sbits; SF = k & ((1u << p.key_sbits) - 1u);
+  } else {
+    const unsigned long long k = reinterpret_cast<const unsigned long long*>(LEAN_KEYOF(p, c))[id];
+    P = (uint32_t)(k >> 32); SF = (uint32_t)k;
+  }
+}
 
 // ── table access ──
-__device__ __forceinline__ uint32_t lean_dense_index(const SearchParams& p, unsigned long long K) {
-  return (uint32_t)(K >> 32) * p.dense_stride + (uint32_t)K;
-}
-// Find the record of key K: position and contents; id == kNone <=> not present (hash: `pos` is then the
-// empty slot that ended the probe — pass it to lean_claim before storing).
+// Find the record of key (P, SF): position and contents; id == kNone <=> not present (hash: `pos` is then
+// the empty slot that ended the probe — pass it to lean_claim before storing).
 template <bool DENSE>
-__device__ __forceinline__ void lean_lookup(const SearchParams& p, const LeanCtx& c, unsigned long long K, uint32_t& pos, double& dist,
+__device__ __forceinline__ void lean_lookup(const SearchParams& p, const LeanCtx& c, uint32_t P, uint32_t SF, uint32_t& pos, double& dist,
                                             uint32_t& id, uint32_t& prev) {
   if (DENSE) {
-    pos = lean_dense_index(p, K);
+    pos = P * p.dense_stride + SF;
     const uint4 v = *reinterpret_cast<const uint4*>(c.base + (uint64_t)pos * 16);
     dist = __hiloint2double((int)v.y, (int)v.x); id = v.z; prev = v.w;
   } else {
+    const unsigned long long K = ((unsigned long long)P << 32) | SF;
     const LeanSlot* tab = reinterpret_cast<const LeanSlot*>(c.base);
     const uint32_t cap = (uint32_t)p.tab_entries;
     uint32_t i = (uint32_t)(((unsigned long long)hash_key(K) * cap) >> 32);
@@ -170,11 +190,12 @@ __device__ __forceinline__ void lean_lookup(const SearchParams& p, const LeanCtx
     }
   }
 }
-// Hash table: claim a slot for the new key K, starting at the empty position the probe found (other
+// Hash table: claim a slot for the new key, starting at the empty position the probe found (other
 // lanes of the group insert other keys concurrently).  Dense table: nothing to do.
 template <bool DENSE>
-__device__ __forceinline__ uint32_t lean_claim(const SearchParams& p, const LeanCtx& c, unsigned long long K, uint32_t pos) {
+__device__ __forceinline__ uint32_t lean_claim(const SearchParams& p, const LeanCtx& c, uint32_t P, uint32_t SF, uint32_t pos) {
   if (DENSE) return pos;
+  const unsigned long long K = ((unsigned long long)P << 32) | SF;
   LeanSlot* tab = reinterpret_cast<LeanSlot*>(c.base);
   const uint32_t cap = (uint32_t)p.tab_entries;
   for (;;) {
@@ -185,20 +206,21 @@ __device__ __forceinline__ uint32_t lean_claim(const SearchParams& p, const Lean
 // Write a record.  The hash variant rewrites the key half too: plain stores keep this SM's L1 copy of the
 // sector consistent with what later plain-load probes must see (the claiming CAS acts on L2 only).
 template <bool DENSE>
-__device__ __forceinline__ void lean_store(const LeanCtx& c, uint32_t pos, unsigned long long K, double dist, uint32_t id, uint32_t prev) {
+__device__ __forceinline__ void lean_store(const LeanCtx& c, uint32_t pos, uint32_t P, uint32_t SF, double dist, uint32_t id, uint32_t prev) {
   const uint4 v = make_uint4((uint32_t)__double2loint(dist), (uint32_t)__double2hiint(dist), id, prev);
   if (DENSE) {
     *reinterpret_cast<uint4*>(c.base + (uint64_t)pos * 16) = v;
   } else {
     uint4* sl = reinterpret_cast<uint4*>(c.base + (uint64_t)pos * 32);
-    sl[0] = make_uint4((uint32_t)K, (uint32_t)(K >> 32), 0u, 0u);
+    sl[0] = make_uint4(SF, P, 0u, 0u);
     sl[1] = v;
   }
 }
 template <bool DENSE>
 __device__ __forceinline__ double lean_dist_of_id(const SearchParams& p, const LeanCtx& c, uint32_t id) {
-  uint32_t pos, i2, pr; double d;
-  lean_lookup<DENSE>(p, c, LEAN_KEYOF(p, c)[id], pos, d, i2, pr);
+  uint32_t P, SF, pos, i2, pr; double d;
+  lean_keyof_load<DENSE>(p, c, id, P, SF);
+  lean_lookup<DENSE>(p, c, P, SF, pos, d, i2, pr);
   return d;
 }
 
@@ -235,7 +257,7 @@ __device__ __forceinline__ void lean_window_evict(const SearchParams& p, const G
   g.sync();
 }
 // Load the lowest non-empty line into the window.  False: the ready set is empty.
-template <int G>
+template <int G, bool DENSE>
 __device__ __forceinline__ bool lean_window_next(const SearchParams& p, const Group<G>& g, const LeanCtx& c, LeanState& st) {
   const uint32_t words = min(p.n1, (st.n_tuples >> (10 + LgG<G>::v)) + 1u);
   uint32_t* l1 = LEAN_L1(c, G);
@@ -253,10 +275,11 @@ __device__ __forceinline__ bool lean_window_next(const SearchParams& p, const Gr
       const uint32_t w = __ldcg(wp);
       if (w) __stcg(wp, 0u);
       LEAN_WIN(c)[g.lane] = w;
-      // the keys of this line are read one pop at a time: pull them into L1 now (32*G ids * 8 B)
-      const char* kp = reinterpret_cast<const char*>(LEAN_KEYOF(p, c) + (uint64_t)line * 32 * G) + (size_t)g.lane * 128;
+      // the keys of this line are read one pop at a time: pull them into L1 now (32*G ids, 4 or 8 B each)
+      constexpr uint32_t kKeyBytes = DENSE ? 4u : 8u;
+      const char* kp = reinterpret_cast<const char*>(LEAN_KEYOF(p, c)) + (uint64_t)line * 32 * G * kKeyBytes + (size_t)g.lane * 128;
 #pragma unroll
-      for (int r = 0; r < 2; r++) asm volatile("prefetch.global.L1 [%0];" ::"l"(kp + (size_t)r * G * 128));
+      for (uint32_t r = 0; r < kKeyBytes / 4; r++) asm volatile("prefetch.global.L1 [%0];" ::"l"(kp + (size_t)r * G * 128));
       g.sync();
       return true;
     }
@@ -291,7 +314,7 @@ __device__ __forceinline__ uint32_t lean_chunk_alloc(const SearchParams& p, cons
     ch = cn;
     if (g.lane == 0) cold[kcChunkNext] = cn + 1;
   } else {
-    st.overflow = true; ch = 0;
+    st.heap_overflow = true; ch = 0;
   }
   g.sync();
   return ch;
@@ -328,7 +351,7 @@ __device__ __forceinline__ void lean_bucket_push(const SearchParams& p, const Gr
     if (left == 0) cnt += k;
     while (left > 0) {
       const uint32_t ch = lean_chunk_alloc<G>(p, g, c, st);
-      if (st.overflow) return;
+      if (st.heap_overflow) return;
       const uint32_t take = left < kChunkIds ? left : kChunkIds;
       if (g.lane == 0) chunks[(uint64_t)ch * 32] = head;
       if (mine && rank >= done && rank < done + take) chunks[(uint64_t)ch * 32 + 1 + (rank - done)] = id;
@@ -349,39 +372,37 @@ __device__ __forceinline__ unsigned long long lean_group_min_u64(const Group<G>&
   return v;
 }
 
-// Build the radix heap from the bag (or, if the bag was abandoned, from all tuples).
+// Build the radix heap: every tuple whose distance is above the level just finished is unsettled and
+// belongs to the future set (one scan, once per string, only if a second level is needed).
 template <int G, bool DENSE>
 __device__ __forceinline__ void lean_build_radix(const SearchParams& p, const Group<G>& g, const LeanCtx& c, LeanState& st) {
   st.sorted = true;
-  const uint32_t n = st.lossy ? st.n_tuples : st.bag_len;
-  for (uint32_t base = 0; base < n && !st.overflow; base += G) {
+  const uint32_t n = st.n_tuples;
+  for (uint32_t base = 0; base < n && !st.heap_overflow; base += G) {
     const uint32_t j = base + g.lane;
-    bool valid = false; uint32_t id = 0; unsigned long long k = 0;
+    bool valid = false; unsigned long long k = 0;
     if (j < n) {
-      id = st.lossy ? j : LEAN_BAG(p, c)[j];
-      k = (unsigned long long)__double_as_longlong(lean_dist_of_id<DENSE>(p, c, id));
+      k = (unsigned long long)__double_as_longlong(lean_dist_of_id<DENSE>(p, c, j));
       valid = k > st.last;
     }
-    if (g.any(valid)) lean_bucket_push<G>(p, g, c, st, valid, id, valid ? bucket_of(k, st.last) : 1u);
+    if (g.any(valid)) lean_bucket_push<G>(p, g, c, st, valid, j, valid ? bucket_of(k, st.last) : 1u);
   }
-  st.bag_len = 0; st.lossy = false;
 }
 
 // Advance to the next distance level; false = the search is finished (no valid entry left, or no
 // remaining tuple can change the result).
 template <int G, bool DENSE>
-__device__ __forceinline__ bool lean_advance_level(const SearchParams& p, const Group<G>& g, const LeanCtx& c, LeanState& st,
-                                                   unsigned long long future_min) {
+__device__ __forceinline__ bool lean_advance_level(const SearchParams& p, const Group<G>& g, const LeanCtx& c, LeanState& st) {
   const uint32_t* cold = LEAN_COLD(p, c, G);
   const bool have_best = cold[kcHaveBest] != 0;
   const double best_total = __hiloint2double((int)cold[kcBestTotHi], (int)cold[kcBestTotLo]);
   if (!st.sorted) {
-    const unsigned long long fm = lean_group_min_u64<G>(g, future_min);
+    const unsigned long long fm = lean_group_min_u64<G>(g, st.future_min);
     if (fm == ~0ull) return false;   // nothing was ever pushed beyond the levels already done
     // lower bound of every remaining distance: cannot reach or tie the best total -> done
     if (!p.exhaustive && have_best && __longlong_as_double((long long)fm) > best_total) return false;
     lean_build_radix<G, DENSE>(p, g, c, st);
-    if (st.overflow) return false;
+    if (st.heap_overflow) return false;
   }
   uint32_t* chunks = LEAN_CHUNKS(p, c);
   for (;;) {
@@ -424,10 +445,10 @@ __device__ __forceinline__ bool lean_advance_level(const SearchParams& p, const 
     const unsigned long long old_last = st.last;
     st.last = m;
     uint32_t ch = hb.x, cnt = hb.y;
-    while (ch != kNoChunk && !st.overflow) {
+    while (ch != kNoChunk && !st.heap_overflow) {
       const uint32_t* cp = chunks + (uint64_t)ch * 32;
       const uint32_t next = cp[0];
-      for (uint32_t o = 0; o < cnt && !st.overflow; o += G) {
+      for (uint32_t o = 0; o < cnt && !st.heap_overflow; o += G) {
         bool valid = false; uint32_t id = 0; unsigned long long k = 0;
         if (o + g.lane < cnt) {
           id = cp[1 + o + g.lane];
@@ -441,7 +462,7 @@ __device__ __forceinline__ bool lean_advance_level(const SearchParams& p, const 
       lean_chunk_free<G>(p, g, c, ch);   // recycle
       ch = next; cnt = kChunkIds;
     }
-    return !st.overflow;
+    return !st.heap_overflow;
   }
 }
 
@@ -452,12 +473,11 @@ __device__ __forceinline__ bool lean_advance_level(const SearchParams& p, const 
 // :182-202 before input-epsilon arcs :254-278); only used to number newly discovered tuples.
 template <int G, bool DENSE>
 __device__ __forceinline__ void lean_relax(const SearchParams& p, const Group<G>& g, const LeanCtx& c, LeanState& st, uint32_t cur_id,
-                                           uint32_t n_cand, bool active, unsigned long long K, double wmin, unsigned first,
-                                           unsigned long long& future_min) {
+                                           uint32_t n_cand, bool active, uint32_t P, uint32_t SF, double wmin, unsigned first) {
   if (n_cand == 0) return;
   st.relax_calls += n_cand;
   uint32_t pos = 0, old_id = 0, old_prev = kNone; double old_dist = d_inf();
-  if (active) lean_lookup<DENSE>(p, c, K, pos, old_dist, old_id, old_prev);
+  if (active) lean_lookup<DENSE>(p, c, P, SF, pos, old_dist, old_id, old_prev);
   // smallest new distance over the parallel arcs (fl(c + w) is monotone in w)
   const double nd = __longlong_as_double((long long)st.last) + wmin;
   const bool is_new = active && old_id == kNone;
@@ -472,41 +492,27 @@ __device__ __forceinline__ void lean_relax(const SearchParams& p, const Group<G>
       const bool in_first = (first >> g.lane) & 1u;
       const uint32_t rank = in_first ? __popc(newmask & first & lt) : (__popc(newmask & first) + __popc(newmask & ~first & lt));
       my_id = st.n_tuples + rank;   // discovery order == reference expansion order (:80-87)
-      LEAN_KEYOF(p, c)[my_id] = K;
-      pos = lean_claim<DENSE>(p, c, K, pos);
+      lean_keyof_store<DENSE>(p, c, my_id, P, SF);
+      pos = lean_claim<DENSE>(p, c, P, SF, pos);
     }
     lowered = is_new || nd < old_dist;                                                         // :109-114, :137-142
     const bool take = lowered || (nd == old_dist && (old_prev == kNone || cur_id < old_prev)); // :115-126
-    if (take) lean_store<DENSE>(c, pos, K, nd, my_id, cur_id);
+    if (take) lean_store<DENSE>(c, pos, P, SF, nd, my_id, cur_id);
   }
   st.n_tuples += n_new;
   // queue: ready set if at the current level, else future set
   const unsigned long long k = (unsigned long long)__double_as_longlong(nd);
-  const bool to_ready = lowered && k == st.last;
+  lean_ready_insert<G>(p, g, c, st, lowered && k == st.last, my_id);
   const bool to_future = lowered && k != st.last;
-  lean_ready_insert<G>(p, g, c, st, to_ready, my_id);
-  const unsigned f = g.ballot(to_future);
-  if (f) {
-    if (to_future && k < future_min) future_min = k;
-    if (st.sorted) {
-      lean_bucket_push<G>(p, g, c, st, to_future, my_id, to_future ? bucket_of(k, st.last) : 1u);
-    } else if (!st.lossy) {
-      const uint32_t cnt = __popc(f);
-      if (st.bag_len + cnt <= p.bag_cap) {
-        if (to_future) LEAN_BAG(p, c)[st.bag_len + __popc(f & g.lt_mask())] = my_id;
-        st.bag_len += cnt;
-      } else {
-        st.lossy = true;   // bag abandoned; a rescan of all tuples rebuilds the future set if ever needed
-      }
-    }
-    g.sync();
+  if (to_future && k < st.future_min) st.future_min = k;
+  if (st.sorted) {
+    if (g.any(to_future)) lean_bucket_push<G>(p, g, c, st, to_future, my_id, to_future ? bucket_of(k, st.last) : 1u);
   }
 }
 
 // Recover the arc of the step prev -> tuple (see file header).  Returns false if none fits (internal error).
-__device__ inline bool lean_recover_arc(const DevFstView& F, const LhsBytes& lhs, unsigned long long Ku, unsigned long long Kv, double du,
-                                        double dv, PoolArc& out) {
-  const uint32_t pu = lean_key_p(Ku), su = lean_key_s(Ku), pv = lean_key_p(Kv), sv = lean_key_s(Kv);
+__device__ inline bool lean_recover_arc(const DevFstView& F, const LhsBytes& lhs, uint32_t pu, uint32_t su, uint32_t pv, uint32_t sv,
+                                        double du, double dv, PoolArc& out) {
   const uint4 rec = __ldg(&F.state_rec[su]);
   uint32_t lo, hi, il = 0;
   const bool match = pv == pu + 1;
@@ -529,134 +535,139 @@ __device__ inline bool lean_recover_arc(const DevFstView& F, const LhsBytes& lhs
   return false;
 }
 
+// Start a string: initial tuple id 0, dist One, ready at level 0 (compose-shortest-path.zig:146-153).
+// Precondition (invariant between strings): table untouched-state, ready bitmap, window and summary zero.
 template <int G, bool DENSE>
-__device__ __forceinline__ int32_t search_lean(const SearchParams& p, const LhsBytes& lhs, const LeanCtx& c, uint32_t* out_path_len,
-                                               uint64_t* out_pool_off, double* out_final_w, uint32_t* out_n_tuples,
-                                               unsigned long long* out_relax) {
-  const Group<G> g;
-  LeanState st;
-  st.n_tuples = 0; st.bag_len = 0; st.wline = 0; st.relax_calls = 0; st.last = 0;
-  st.low_pending = false; st.overflow = false; st.sorted = false; st.lossy = false;
-  unsigned long long future_min = ~0ull;
-  unsigned long long relax_hi = 0;   // relax calls beyond 31 bits (flushed rarely)
-  *out_path_len = 0; *out_pool_off = 0; *out_final_w = d_inf(); *out_n_tuples = 0; *out_relax = 0;
-  const DevFstView& F = p.fst;
-  if (F.start == kNone) return kStNoPath;
-  unsigned long long* key_of = LEAN_KEYOF(p, c);
+__device__ __forceinline__ void lean_begin(const SearchParams& p, const Group<G>& g, const LeanCtx& c, LeanState& st) {
+  st.n_tuples = 1; st.wline = 0; st.relax_calls = 0; st.last = 0; st.future_min = ~0ull; st.relax_hi = 0;
+  st.low_pending = false; st.overflow = false; st.heap_overflow = false; st.sorted = false;
   uint32_t* cold = LEAN_COLD(p, c, G);
-
-  // initial tuple: id 0, dist One, ready at level 0 (compose-shortest-path.zig:146-153)
   if (g.lane == 0) {
-    const unsigned long long k0 = lean_key(0, F.start, 0);
+    const uint32_t SF = p.fst.start << 1;
     uint32_t pos, id, prev; double d;
-    lean_lookup<DENSE>(p, c, k0, pos, d, id, prev);
-    pos = lean_claim<DENSE>(p, c, k0, pos);
-    lean_store<DENSE>(c, pos, k0, 0.0, 0u, kNone);
-    key_of[0] = k0;
+    lean_lookup<DENSE>(p, c, 0u, SF, pos, d, id, prev);
+    pos = lean_claim<DENSE>(p, c, 0u, SF, pos);
+    lean_store<DENSE>(c, pos, 0u, SF, 0.0, 0u, kNone);
+    lean_keyof_store<DENSE>(p, c, 0u, 0u, SF);
     cold[kcChunkNext] = 0; cold[kcFreeHead] = kNoChunk; cold[kcOccLo] = 0; cold[kcOccHi] = 0; cold[kcHaveBest] = 0;
   }
-  LEAN_WIN(c)[g.lane] = g.lane == 0 ? 1u : 0u;   // window = line 0 (all of l0 is zero between strings)
-  st.n_tuples = 1;
+  LEAN_WIN(c)[g.lane] = g.lane == 0 ? 1u : 0u;   // window = line 0, bit 0
   g.sync();
+}
 
-  for (;;) {
-    if (st.overflow) break;
-    // ── pop the smallest ready id (:159-163; the set only holds unsettled tuples at the level distance) ──
-    if (st.low_pending) { lean_window_evict<G>(p, g, c, st); st.low_pending = false; }
-    const uint32_t w = LEAN_WIN(c)[g.lane];
-    const unsigned bal = g.ballot(w != 0);
-    if (bal == 0) {
-      if (lean_window_next<G>(p, g, c, st)) continue;
-      if (!lean_advance_level<G, DENSE>(p, g, c, st, future_min)) break;
-      continue;
-    }
-    const int src = __ffs(bal) - 1;
-    const uint32_t ww = g.shfl(w, src);
-    const uint32_t cur_id = ((st.wline * G + src) << 5) + (__ffs(ww) - 1);
-    if ((int)g.lane == src) LEAN_WIN(c)[src] = ww & (ww - 1);
-    g.sync();
-    const unsigned long long ckey = key_of[cur_id];
-    const uint32_t s1 = lean_key_p(ckey), s2 = lean_key_s(ckey);
-
-    // final check (:165-179): only the last state of the string acceptor is final, weight One
-    if (s1 == lhs.len) {
-      const double fw2 = F.final_w[s2];
-      if (!d_isinf(fw2)) {
-        const double final_w = 0.0 + fw2;
-        const double total = __longlong_as_double((long long)st.last) + final_w;
-        const bool have_best = cold[kcHaveBest] != 0;
-        const double best_total = __hiloint2double((int)cold[kcBestTotHi], (int)cold[kcBestTotLo]);
-        const uint32_t best_id = cold[kcBestId];
-        g.sync();
-        if (!have_best || total < best_total || (total == best_total && cur_id < best_id)) {
-          if (g.lane == 0) {
-            cold[kcHaveBest] = 1; cold[kcBestId] = cur_id;
-            cold[kcBestFwLo] = (uint32_t)__double2loint(final_w); cold[kcBestFwHi] = (uint32_t)__double2hiint(final_w);
-            cold[kcBestTotLo] = (uint32_t)__double2loint(total); cold[kcBestTotHi] = (uint32_t)__double2hiint(total);
-          }
-        }
-        g.sync();
-      }
-    }
-    // ── expansion (:182-202 match arcs, then :254-278 input-epsilon arcs; filter is 0 or 1 here) ──
-    const uint4 rec = __ldg(&F.state_rec[s2]);   // {arc_begin, eps_end, arc_end}
-    const uint32_t deg = rec.z - rec.x;
-    const uint32_t x = s1 < lhs.len ? (uint32_t)__ldg(lhs.s + s1) + 1u : 0xFFFFFFFEu;
-    if (deg <= (uint32_t)G) {
-      // one lane per arc of the state, in frozen order (epsilon prefix first)
-      const uint32_t arc = rec.x + g.lane;
-      uint4 sa = make_uint4(0xFFFFFFFFu, 0x80000000u, 0, 0);
-      if (g.lane < deg) sa = __ldg(&F.sarc[arc]);
-      const bool is_match = sa.x == x;               // idle lanes hold ilabel 0xFFFFFFFF, x is never that
-      const bool is_eps = arc < rec.y;               // the epsilon prefix [arc_begin, eps_end)
-      const uint32_t nxt = sa.y & 0x7FFFFFFFu;
-      const unsigned long long K = is_match ? lean_key(s1 + 1u, nxt, 0u) : lean_key(s1, nxt, 1u);
-      const unsigned first = g.ballot(is_match);
-      lean_relax<G, DENSE>(p, g, c, st, cur_id, __popc(first) + (rec.y - rec.x), (is_match || is_eps) && !(sa.y >> 31), K,
-                           __hiloint2double((int)sa.w, (int)sa.z), first, future_min);
-    } else {
-      uint32_t lo = 0, hi = 0;
-      if (s1 < lhs.len) equal_range(g, F.ilabel, rec.x, rec.z, x, lo, hi);
-      for (uint32_t cb = lo; cb < hi && !st.overflow; cb += G) {
-        const bool cand = cb + g.lane < hi;
-        uint4 sa = make_uint4(0, 0x80000000u, 0, 0);
-        if (cand) sa = __ldg(&F.sarc[cb + g.lane]);
-        lean_relax<G, DENSE>(p, g, c, st, cur_id, min(hi - cb, (uint32_t)G), cand && !(sa.y >> 31), lean_key(s1 + 1u, sa.y & 0x7FFFFFFFu, 0u),
-                             __hiloint2double((int)sa.w, (int)sa.z), Group<G>::kBits, future_min);
-        g.sync();
-      }
-      for (uint32_t cb = rec.x; cb < rec.y && !st.overflow; cb += G) {
-        const bool cand = cb + g.lane < rec.y;
-        uint4 sa = make_uint4(0, 0x80000000u, 0, 0);
-        if (cand) sa = __ldg(&F.sarc[cb + g.lane]);
-        lean_relax<G, DENSE>(p, g, c, st, cur_id, min(rec.y - cb, (uint32_t)G), cand && !(sa.y >> 31), lean_key(s1, sa.y & 0x7FFFFFFFu, 1u),
-                             __hiloint2double((int)sa.w, (int)sa.z), Group<G>::kBits, future_min);
-        g.sync();
-      }
-    }
-    if (st.relax_calls >= 0x80000000u) { relax_hi += st.relax_calls; st.relax_calls = 0; }
+// One step of a string: pop the smallest ready id and expand it, or (rarely) switch the window / advance
+// the level.  False: the search is over (queue empty, early stop, or an overflow).
+template <int G, bool DENSE>
+__device__ __forceinline__ bool lean_step(const SearchParams& p, const Group<G>& g, const LeanCtx& c, LeanState& st, const LhsBytes& lhs) {
+  if (st.overflow || st.heap_overflow) return false;
+  // ── pop the smallest ready id (:159-163; the set only holds unsettled tuples at the level distance) ──
+  if (st.low_pending) { lean_window_evict<G>(p, g, c, st); st.low_pending = false; }
+  const uint32_t w = LEAN_WIN(c)[g.lane];
+  const unsigned bal = g.ballot(w != 0);
+  if (bal == 0) {
+    if (lean_window_next<G, DENSE>(p, g, c, st)) return true;
+    return lean_advance_level<G, DENSE>(p, g, c, st);
   }
+  const DevFstView& F = p.fst;
+  const int src = __ffs(bal) - 1;
+  const uint32_t ww = g.shfl(w, src);
+  const uint32_t cur_id = ((st.wline * G + src) << 5) + (__ffs(ww) - 1);
+  if ((int)g.lane == src) LEAN_WIN(c)[src] = ww & (ww - 1);
+  g.sync();
+  uint32_t s1, sf;
+  lean_keyof_load<DENSE>(p, c, cur_id, s1, sf);
+  const uint32_t s2 = sf >> 1;
 
+  // final check (:165-179): only the last state of the string acceptor is final, weight One
+  if (s1 == lhs.len) {
+    const double fw2 = F.final_w[s2];
+    if (!d_isinf(fw2)) {
+      uint32_t* cold = LEAN_COLD(p, c, G);
+      const double final_w = 0.0 + fw2;
+      const double total = __longlong_as_double((long long)st.last) + final_w;
+      const bool have_best = cold[kcHaveBest] != 0;
+      const double best_total = __hiloint2double((int)cold[kcBestTotHi], (int)cold[kcBestTotLo]);
+      const uint32_t best_id = cold[kcBestId];
+      g.sync();
+      if (!have_best || total < best_total || (total == best_total && cur_id < best_id)) {
+        if (g.lane == 0) {
+          cold[kcHaveBest] = 1; cold[kcBestId] = cur_id;
+          cold[kcBestFwLo] = (uint32_t)__double2loint(final_w); cold[kcBestFwHi] = (uint32_t)__double2hiint(final_w);
+          cold[kcBestTotLo] = (uint32_t)__double2loint(total); cold[kcBestTotHi] = (uint32_t)__double2hiint(total);
+        }
+      }
+      g.sync();
+    }
+  }
+  // ── expansion (:182-202 match arcs, then :254-278 input-epsilon arcs; filter is 0 or 1 here) ──
+  const uint4 rec = __ldg(&F.state_rec[s2]);   // {arc_begin, eps_end, arc_end}
+  const uint32_t deg = rec.z - rec.x;
+  const uint32_t x = s1 < lhs.len ? (uint32_t)__ldg(lhs.s + s1) + 1u : 0xFFFFFFFEu;
+  if (deg <= (uint32_t)G) {
+    // one lane per arc of the state, in frozen order (epsilon prefix first)
+    const uint32_t arc = rec.x + g.lane;
+    uint4 sa = make_uint4(0xFFFFFFFFu, 0x80000000u, 0, 0);
+    if (g.lane < deg) sa = __ldg(&F.sarc[arc]);
+    const bool is_match = sa.x == x;               // idle lanes hold ilabel 0xFFFFFFFF, x is never that
+    const bool is_eps = arc < rec.y;               // the epsilon prefix [arc_begin, eps_end)
+    const unsigned first = g.ballot(is_match);
+    lean_relax<G, DENSE>(p, g, c, st, cur_id, __popc(first) + (rec.y - rec.x), (is_match || is_eps) && !(sa.y >> 31),
+                         is_match ? s1 + 1u : s1, (sa.y << 1) | (is_match ? 0u : 1u), __hiloint2double((int)sa.w, (int)sa.z), first);
+  } else {
+    uint32_t lo = 0, hi = 0;
+    if (s1 < lhs.len) equal_range(g, F.ilabel, rec.x, rec.z, x, lo, hi);
+    for (uint32_t cb = lo; cb < hi && !st.overflow && !st.heap_overflow; cb += G) {
+      const bool cand = cb + g.lane < hi;
+      uint4 sa = make_uint4(0, 0x80000000u, 0, 0);
+      if (cand) sa = __ldg(&F.sarc[cb + g.lane]);
+      lean_relax<G, DENSE>(p, g, c, st, cur_id, min(hi - cb, (uint32_t)G), cand && !(sa.y >> 31), s1 + 1u, sa.y << 1,
+                           __hiloint2double((int)sa.w, (int)sa.z), Group<G>::kBits);
+      g.sync();
+    }
+    for (uint32_t cb = rec.x; cb < rec.y && !st.overflow && !st.heap_overflow; cb += G) {
+      const bool cand = cb + g.lane < rec.y;
+      uint4 sa = make_uint4(0, 0x80000000u, 0, 0);
+      if (cand) sa = __ldg(&F.sarc[cb + g.lane]);
+      lean_relax<G, DENSE>(p, g, c, st, cur_id, min(rec.y - cb, (uint32_t)G), cand && !(sa.y >> 31), s1, (sa.y << 1) | 1u,
+                           __hiloint2double((int)sa.w, (int)sa.z), Group<G>::kBits);
+      g.sync();
+    }
+  }
+  if (st.relax_calls >= 0x80000000u) { st.relax_hi += st.relax_calls; st.relax_calls = 0; }
+  return true;
+}
+
+// End of a string: back-track, emit the reversed path into the pool, restore the arena invariants.
+template <int G, bool DENSE>
+__device__ __forceinline__ int32_t lean_finish(const SearchParams& p, const Group<G>& g, const LeanCtx& c, const LeanState& st,
+                                               const LhsBytes& lhs, uint32_t* out_path_len, uint64_t* out_pool_off, double* out_final_w) {
+  const DevFstView& F = p.fst;
+  uint32_t* cold = LEAN_COLD(p, c, G);
   int32_t status = kStPath;
   uint32_t plen = 0;
   unsigned long long poff = 0;
-  uint32_t* scratch = LEAN_BAG(p, c);   // the future set is dead now; bag_cap >= tuple_cap by construction
+  uint32_t* scratch = LEAN_CHUNKS(p, c);   // the future set is dead now
+  const uint32_t scratch_cap = p.heap_cap * 32u;
   g.sync();
   const bool have_best = cold[kcHaveBest] != 0;
   const uint32_t best_id = cold[kcBestId];
   const double best_fw = __hiloint2double((int)cold[kcBestFwHi], (int)cold[kcBestFwLo]);
   if (st.overflow) {
     status = kStRetry;
+  } else if (st.heap_overflow) {
+    status = kStRetryHeap;
   } else if (!have_best) {
     status = kStNoPath;                                               // :368-370
   } else {
     if (g.lane == 0) {                                                // :372-380 back-track (ids only)
       uint32_t cur = best_id;
       while (cur != 0) {
-        uint32_t pos, id, prev; double d;
-        lean_lookup<DENSE>(p, c, key_of[cur], pos, d, id, prev);
+        uint32_t P, SF, pos, id, prev; double d;
+        lean_keyof_load<DENSE>(p, c, cur, P, SF);
+        lean_lookup<DENSE>(p, c, P, SF, pos, d, id, prev);
         if (prev == kNone) { status = kStNoPath; break; }             // :375-377
         if (plen >= st.n_tuples) { status = kStCycle; break; }        // hazard H1 (reference: out of memory)
+        if (plen >= scratch_cap) { status = kStRetryHeap; break; }
         scratch[plen++] = cur;
         cur = prev;
       }
@@ -670,13 +681,13 @@ __device__ __forceinline__ int32_t search_lean(const SearchParams& p, const LhsB
     if (status == kStPath) {
       bool bad = false;
       for (uint32_t i = g.lane; i < plen; i += G) {
-        const unsigned long long Kv = key_of[scratch[i]];
-        uint32_t pos, id, prev, id2, prev2; double dv, du;
-        lean_lookup<DENSE>(p, c, Kv, pos, dv, id, prev);
-        const unsigned long long Ku = key_of[prev];
-        lean_lookup<DENSE>(p, c, Ku, pos, du, id2, prev2);
+        uint32_t pv, sfv, pu, sfu, pos, id, prev, id2, prev2; double dv, du;
+        lean_keyof_load<DENSE>(p, c, scratch[i], pv, sfv);
+        lean_lookup<DENSE>(p, c, pv, sfv, pos, dv, id, prev);
+        lean_keyof_load<DENSE>(p, c, prev, pu, sfu);
+        lean_lookup<DENSE>(p, c, pu, sfu, pos, du, id2, prev2);
         PoolArc pa; pa.ilabel = 0; pa.olabel = 0; pa.weight = 0.0;
-        if (!lean_recover_arc(F, lhs, Ku, Kv, du, dv, pa)) bad = true;
+        if (!lean_recover_arc(F, lhs, pu, sfu >> 1, pv, sfv >> 1, du, dv, pa)) bad = true;
         p.pool[poff + i] = pa;
       }
       if (g.any(bad)) { status = kStInternal; plen = 0; }
@@ -689,19 +700,23 @@ __device__ __forceinline__ int32_t search_lean(const SearchParams& p, const LhsB
   const uint32_t n = st.n_tuples;
   if (DENSE) {
     if ((uint64_t)n * 4 < p.tab_entries) {
-      for (uint32_t i = g.lane; i < n; i += G)
-        *reinterpret_cast<uint4*>(c.base + (uint64_t)lean_dense_index(p, key_of[i]) * 16) = make_uint4(~0u, ~0u, ~0u, ~0u);
+      for (uint32_t i = g.lane; i < n; i += G) {
+        uint32_t P, SF;
+        lean_keyof_load<true>(p, c, i, P, SF);
+        *reinterpret_cast<uint4*>(c.base + (uint64_t)(P * p.dense_stride + SF) * 16) = make_uint4(~0u, ~0u, ~0u, ~0u);
+      }
     } else {
       uint4* t = reinterpret_cast<uint4*>(c.base);
       for (uint64_t i = g.lane; i < p.tab_entries; i += G) t[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
     }
   } else {
     // two phases: resolve every tuple's slot first (probing needs intact chains), then clear
+    unsigned long long* key_of = reinterpret_cast<unsigned long long*>(LEAN_KEYOF(p, c));
     uint32_t* slot_tmp = reinterpret_cast<uint32_t*>(key_of);
     for (uint32_t base = 0; base < n; base += G) {
       const uint32_t i = base + g.lane;
       uint32_t sl = 0, id, prev; double d;
-      if (i < n) lean_lookup<false>(p, c, key_of[i], sl, d, id, prev);
+      if (i < n) { const unsigned long long K = key_of[i]; lean_lookup<false>(p, c, (uint32_t)(K >> 32), (uint32_t)K, sl, d, id, prev); }
       g.sync();                        // all keys of this stripe are read before any is overwritten
       if (i < n) slot_tmp[i] = sl;     // aliases key_of[i/2]: only stripes already resolved
       g.sync();
@@ -709,7 +724,7 @@ __device__ __forceinline__ int32_t search_lean(const SearchParams& p, const LhsB
     LeanSlot* tab = reinterpret_cast<LeanSlot*>(c.base);
     for (uint32_t i = g.lane; i < n; i += G) tab[slot_tmp[i]].key = kEmptyKey;
   }
-  if (st.overflow) {
+  if (st.overflow || st.heap_overflow) {
     // aborted searches can leave ready bits behind
     for (uint32_t i = g.lane; i < ((n + 32u * G - 1) / (32u * G)) * G; i += G) LEAN_L0(p, c)[i] = 0;
     for (uint32_t i = g.lane; i < p.n1; i += G) LEAN_L1(c, G)[i] = 0;
@@ -717,11 +732,12 @@ __device__ __forceinline__ int32_t search_lean(const SearchParams& p, const LhsB
   }
   g.sync();
   *out_path_len = plen; *out_pool_off = poff; *out_final_w = (status == kStPath) ? best_fw : d_inf();
-  *out_n_tuples = st.n_tuples; *out_relax = relax_hi + st.relax_calls;
   return status;
 }
 
-// Persistent batch kernel: every G-lane group pulls strings from a global queue.
+// Persistent batch kernel.  One loop; an iteration is one step of this group's string (fetch the next
+// string / one pop / finish), with a warp-wide reconvergence at the top so that the 16-lane groups of a
+// warp stay in lockstep.
 template <int G, bool DENSE>
 __global__ void __launch_bounds__(128, FSTB_LEAN_MINBLOCKS) csp_batch_lean_kernel(const __grid_constant__ SearchParams p) {
   extern __shared__ __align__(16) uint32_t smem_all[];
@@ -733,20 +749,45 @@ __global__ void __launch_bounds__(128, FSTB_LEAN_MINBLOCKS) csp_batch_lean_kerne
   c.sm = smem_all + (size_t)gib * p.smem_words;
   for (uint32_t i = 128 + g.lane; i < p.smem_words; i += G) c.sm[i] = 0;   // window, summary and cold state start empty
   g.sync();
+  enum { kFetch = 0, kRun = 1, kFinish = 2, kDone = 3 };
+  uint32_t phase = kFetch, idx = 0;
+  LeanState st;
+  LhsBytes lhs; lhs.s = nullptr; lhs.len = 0;
   unsigned long long relax_total = 0, tuple_total = 0;
   for (;;) {
-    uint32_t item = 0;
-    if (g.lane == 0) item = atomicAdd(p.queue_head, 1u);
-    item = g.shfl(item, 0);
-    if (item >= p.n_items) break;
-    const uint32_t idx = p.order ? p.order[item] : item;
-    LhsBytes lhs; lhs.s = p.bytes + p.offsets[idx]; lhs.len = (uint32_t)(p.offsets[idx + 1] - p.offsets[idx]);
-    uint32_t plen; uint64_t poff; double fw; uint32_t nt; unsigned long long nr;
-    const int32_t status = search_lean<G, DENSE>(p, lhs, c, &plen, &poff, &fw, &nt, &nr);
-    if (g.lane == 0) {
-      p.status[idx] = status; p.path_len[idx] = plen; p.pool_off[idx] = poff; p.final_w[idx] = fw; p.n_tuples[idx] = nt;
+    if (G < 32) {
+      __syncwarp();
+      if (__all_sync(0xFFFFFFFFu, phase == kDone)) break;
+    } else if (phase == kDone) {
+      break;
     }
-    relax_total += nr; tuple_total += nt;
+    if (phase == kRun) {
+      if (!lean_step<G, DENSE>(p, g, c, st, lhs)) phase = kFinish;
+    } else if (phase == kFetch) {
+      uint32_t item = 0;
+      if (g.lane == 0) item = atomicAdd(p.queue_head, 1u);
+      item = g.shfl(item, 0);
+      if (item >= p.n_items) {
+        phase = kDone;
+      } else {
+        idx = p.order ? p.order[item] : item;
+        lhs.s = p.bytes + p.offsets[idx]; lhs.len = (uint32_t)(p.offsets[idx + 1] - p.offsets[idx]);
+        if (p.fst.start == kNone) {
+          if (g.lane == 0) { p.status[idx] = kStNoPath; p.path_len[idx] = 0; p.pool_off[idx] = 0; p.final_w[idx] = d_inf(); p.n_tuples[idx] = 0; }
+        } else {
+          lean_begin<G, DENSE>(p, g, c, st);
+          phase = kRun;
+        }
+      }
+    } else if (phase == kFinish) {
+      uint32_t plen; uint64_t poff; double fw;
+      const int32_t status = lean_finish<G, DENSE>(p, g, c, st, lhs, &plen, &poff, &fw);
+      if (g.lane == 0) {
+        p.status[idx] = status; p.path_len[idx] = plen; p.pool_off[idx] = poff; p.final_w[idx] = fw; p.n_tuples[idx] = st.n_tuples;
+      }
+      relax_total += st.relax_hi + st.relax_calls; tuple_total += st.n_tuples;
+      phase = kFetch;
+    }
   }
   if (g.lane == 0) {
     if (relax_total) atomicAdd(p.relax_counter, relax_total);

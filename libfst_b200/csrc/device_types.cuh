@@ -59,7 +59,7 @@ constexpr uint32_t kSettledBit = 0x80000000u;
 
 // Per-string status written by the search kernel (internal; the C ABI maps
 // kRetry to a retry pass and finally to FST_B200_TOO_LARGE).
-enum : int32_t { kStPath = 0, kStNoPath = 1, kStCycle = 2, kStTooLarge = 3, kStInternal = 4, kStRetry = 100 };
+enum : int32_t { kStPath = 0, kStNoPath = 1, kStCycle = 2, kStTooLarge = 3, kStInternal = 4, kStRetry = 100, kStRetryHeap = 101 };
 
 // Reversed path arc as written to the path pool by the search kernel.
 struct __align__(16) PoolArc { uint32_t ilabel, olabel; double weight; };
@@ -84,10 +84,11 @@ struct SearchParams {
   uint32_t dense;          // lean path: 1 = direct-indexed table, 0 = hash table
   uint64_t tab_entries;    // lean path: dense records ((max_len+1) * S * 2) or hash slots
   // lean path: arena geometry precomputed on the host (read from the constant bank at the point of use)
-  uint64_t off_keyof, off_l0, off_bag, off_chunks;
+  uint64_t off_keyof, off_l0, off_chunks;
   uint32_t n1;             // ready-bitmap summary words
   uint32_t smem_words;     // shared-memory words per group
   uint32_t dense_stride;   // 2 * S: dense index = p * dense_stride + ((s << 1) | filter)
+  uint32_t key_sbits;      // dense: bits of ((s << 1) | filter) in the compact id -> key array
   // work queue + counters
   uint32_t* queue_head;
   unsigned long long* pool_cursor;

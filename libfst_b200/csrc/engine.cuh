@@ -49,6 +49,7 @@ struct DeviceFst {
   bool serial = false;     // negative weights: literal sequential relax
   bool lean_ok = false;    // all arc weights finite and >= 0: the lean batched kernel applies
   uint32_t hint_tuples = 0;  // largest per-string tuple count seen so far (arena sizing)
+  uint32_t hint_heap_mult = 1;  // radix-heap pool depth that sufficed so far (lean kernel)
 };
 
 inline cudaError_t upload_fst(const HostFrozen& f, int device, DeviceFst** out) {
@@ -135,13 +136,16 @@ inline void free_device_fst(DeviceFst* d) {
 }
 
 // small helper kernels (plumbing)
-__global__ void collect_retry_kernel(const int32_t* status, uint32_t n, uint32_t* order, uint32_t* count) {
+__global__ void collect_retry_kernel(const int32_t* status, uint32_t n, uint32_t* order, uint32_t* count, uint32_t* heap_count) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n && status[i] == kStRetry) order[atomicAdd(count, 1u)] = i;
+  if (i < n && (status[i] == kStRetry || status[i] == kStRetryHeap)) {
+    order[atomicAdd(count, 1u)] = i;
+    if (status[i] == kStRetryHeap) atomicAdd(heap_count, 1u);
+  }
 }
 __global__ void mark_too_large_kernel(int32_t* status, uint32_t* path_len, uint32_t n) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n && status[i] == kStRetry) { status[i] = kStTooLarge; path_len[i] = 0; }
+  if (i < n && (status[i] == kStRetry || status[i] == kStRetryHeap)) { status[i] = kStTooLarge; path_len[i] = 0; }
 }
 __global__ void fill_retry_kernel(int32_t* status, uint32_t* path_len, uint32_t n) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -218,7 +222,7 @@ class Engine {
     bc->launches++;
 
     uint32_t tuple_cap = cfg.tuples_hint ? cfg.tuples_hint : (fst->hint_tuples ? fst->hint_tuples + fst->hint_tuples / 4 + 64 : 4096);
-    uint32_t n_items = n, heap_mult = 1;
+    uint32_t n_items = n, heap_mult = fst->hint_heap_mult;
     const uint32_t* d_order = nullptr;
     auto too_large = [&]() {
       mark_too_large_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_status, d_path_len_, n);
@@ -250,9 +254,10 @@ class Engine {
       p.hash_cap = gm.hash_cap; p.tuple_cap = gm.tuple_cap; p.heap_cap = gm.heap_cap; p.bag_cap = gm.bag_cap; p.exhaustive = cfg.exhaustive;
       p.dense = gm.dense ? 1u : 0u; p.tab_entries = gm.tab_entries;
       if (gm.kind == kLean) {
-        const LeanLayout L = lean_layout((int)gm.G, gm.dense, gm.tab_entries, gm.tuple_cap, gm.heap_cap, gm.bag_cap);
-        p.off_keyof = L.off_keyof; p.off_l0 = L.off_l0; p.off_bag = L.off_bag; p.off_chunks = L.off_chunks;
+        const LeanLayout L = lean_layout((int)gm.G, gm.dense, gm.tab_entries, gm.tuple_cap, gm.heap_cap);
+        p.off_keyof = L.off_keyof; p.off_l0 = L.off_l0; p.off_chunks = L.off_chunks;
         p.n1 = L.n1; p.smem_words = L.smem_words; p.dense_stride = fst->view.num_states * 2u;
+        p.key_sbits = 1; while ((1u << p.key_sbits) < p.dense_stride) p.key_sbits++;
       }
       p.queue_head = d_cnt + 0;
       p.pool_cursor = reinterpret_cast<unsigned long long*>(d_cnt + 2);
@@ -265,12 +270,13 @@ class Engine {
       FSTB_CUDA(cudaGetLastError());
       // any string that overflowed its arena (or the pool)?
       FSTB_CUDA(cudaMemsetAsync(d_cnt + 1, 0, 4, stream));
-      collect_retry_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_status, n, d_order_buf_[pass & 1], d_cnt + 1);
+      FSTB_CUDA(cudaMemsetAsync(d_cnt + 9, 0, 4, stream));
+      collect_retry_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_status, n, d_order_buf_[pass & 1], d_cnt + 1, d_cnt + 9);
       bc->launches++;
       FSTB_CUDA(cudaMemcpyAsync(h_small_, d_cnt, 64, cudaMemcpyDeviceToHost, stream));
       FSTB_CUDA(cudaStreamSynchronize(stream));
       const uint32_t* hc = static_cast<const uint32_t*>(h_small_);
-      uint32_t retry = hc[1];
+      const uint32_t retry = hc[1], heap_retry = hc[9];
       unsigned long long pool_used; std::memcpy(&pool_used, hc + 2, 8);
       if (retry == 0) break;
       if (pool_used > pool_cap_) {
@@ -279,13 +285,16 @@ class Engine {
         too_large();
         break;
       }
-      // next pass: only the overflowed strings, 8x larger arenas (and a deeper radix-heap pool)
+      // next pass: only the overflowed strings; 8x larger arenas and/or a 4x deeper radix-heap pool
       n_items = retry;
       d_order = d_order_buf_[pass & 1];
-      if (gm.kind == kLean && gm.dense && gm.tuple_cap >= gm.tab_entries) {
-        if (heap_mult >= 64) { too_large(); break; }
+      if (heap_retry > 0) {
+        if (heap_mult >= 16) { too_large(); break; }
         heap_mult *= 4;
-      } else {
+        if (heap_mult > fst->hint_heap_mult) fst->hint_heap_mult = heap_mult;
+      }
+      if (retry > heap_retry) {
+        if (gm.kind == kLean && gm.dense && gm.tuple_cap >= gm.tab_entries) { too_large(); break; }   // cannot happen: N <= records
         if (tuple_cap > (1u << 31) / 8) { too_large(); break; }
         tuple_cap *= 8;
       }
@@ -486,7 +495,7 @@ class Engine {
       if (tuple_cap > kMaxFastTuples) return false;
       g->kind = kWarp; g->G = 32; g->tuple_cap = tuple_cap;
       g->hash_cap = (uint32_t)std::min<uint64_t>(0xFFFFFFF0ull, (uint64_t)tuple_cap * 100 / 65 + 16);
-      g->heap_cap = 96 + (tuple_cap / 24) * heap_mult;   // 128-byte chunks of 31 ids: ~1.3 queued ids per tuple
+      g->heap_cap = 96 + tuple_cap / 24;   // 128-byte chunks of 31 ids: ~1.3 queued ids per tuple
       g->bag_cap = tuple_cap;                             // also the back-track scratch (path <= tuples)
       WarpLayout L = warp_layout(g->hash_cap, g->tuple_cap, g->heap_cap, g->bag_cap);
       g->stride = L.total; g->smem_per_group = L.smem_words * 4;
@@ -508,9 +517,10 @@ class Engine {
     }
     if (tuple_cap > kMaxFastTuples) return false;
     g->tuple_cap = tuple_cap;
-    g->heap_cap = 96 + (tuple_cap / 24) * heap_mult;
-    g->bag_cap = tuple_cap;
-    LeanLayout L = lean_layout((int)g->G, g->dense, g->tab_entries, g->tuple_cap, g->heap_cap, g->bag_cap);
+    // radix-heap pool (128-byte chunks of 31 ids): shallow until a search really needs distance levels
+    g->heap_cap = 96 + (tuple_cap / 96) * heap_mult;
+    g->bag_cap = 0;
+    LeanLayout L = lean_layout((int)g->G, g->dense, g->tab_entries, g->tuple_cap, g->heap_cap);
     g->stride = L.total; g->smem_per_group = L.smem_words * 4;
     g->off_l0 = L.off_l0; g->tab_bytes = L.tab_bytes; g->l0_bytes = L.l0_bytes;
     return true;
@@ -559,7 +569,7 @@ class Engine {
     if (budget_cache_) return budget_cache_;
     size_t fr = 0, tot = 0;
     if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) return 1ull << 30;
-    budget_cache_ = (uint64_t)((fr + workspace_bytes_) * 0.85);
+    budget_cache_ = (uint64_t)((fr + workspace_bytes_) * 0.9);
     return budget_cache_;
   }
   uint64_t budget_cache_ = 0;
