@@ -50,6 +50,7 @@ struct DeviceFst {
   bool lean_ok = false;    // all arc weights finite and >= 0: the lean batched kernel applies
   uint32_t hint_tuples = 0;  // largest per-string tuple count seen so far (arena sizing)
   uint32_t hint_heap_mult = 1;  // radix-heap pool depth that sufficed so far (lean kernel)
+  uint32_t lean_lanes = 32;     // lanes per string of the lean kernel: smallest of 8/16/32 that covers 90% of the states' arcs in one step
 };
 
 inline cudaError_t upload_fst(const HostFrozen& f, int device, DeviceFst** out) {
@@ -123,6 +124,11 @@ inline cudaError_t upload_fst(const HostFrozen& f, int device, DeviceFst** out) 
   d->view.ilabel = reinterpret_cast<const uint32_t*>(base + o_il);
   d->view.payload = reinterpret_cast<const uint4*>(base + o_pl);
   d->view.sarc = reinterpret_cast<const uint4*>(base + o_sa);
+  {
+    uint32_t le8 = 0, le16 = 0;
+    for (uint32_t s = 0; s < S; s++) { le8 += st[s].num_arcs <= 8; le16 += st[s].num_arcs <= 16; }
+    d->lean_lanes = (uint64_t)le8 * 10 >= (uint64_t)S * 9 ? 8 : ((uint64_t)le16 * 10 >= (uint64_t)S * 9 ? 16 : 32);
+  }
   *out = d;
   return cudaSuccess;
 }
@@ -501,7 +507,8 @@ class Engine {
       g->stride = L.total; g->smem_per_group = L.smem_words * 4;
       return true;
     }
-    g->kind = kLean; g->G = cfg.lanes_per_string == 16 ? 16 : 32;
+    g->kind = kLean;
+    g->G = (cfg.lanes_per_string == 8 || cfg.lanes_per_string == 16 || cfg.lanes_per_string == 32) ? cfg.lanes_per_string : fst->lean_lanes;
     const uint64_t E = (uint64_t)(max_len + 1) * fst->view.num_states * 2;
     const bool dense_ok = E < 0xFFFFFF00ull && E * 16 <= kDenseLimitBytes;
     // dense pays when the search touches a good part of the (position x state) grid; a small search keeps its
@@ -538,6 +545,7 @@ class Engine {
   static const void* kernel_ptr(const Geom& g) {
     if (g.kind == kWarp) return (const void*)csp_batch_warp_kernel;
     if (g.kind == kLean) {
+      if (g.G == 8) return g.dense ? (const void*)csp_batch_lean_kernel<8, true> : (const void*)csp_batch_lean_kernel<8, false>;
       if (g.G == 16) return g.dense ? (const void*)csp_batch_lean_kernel<16, true> : (const void*)csp_batch_lean_kernel<16, false>;
       return g.dense ? (const void*)csp_batch_lean_kernel<32, true> : (const void*)csp_batch_lean_kernel<32, false>;
     }
@@ -556,7 +564,8 @@ class Engine {
     const size_t sm = (size_t)(threads / g.G) * g.smem_per_group;
     if (g.kind == kWarp) { csp_batch_warp_kernel<<<blocks, threads, sm, s>>>(p); return; }
     if (g.kind == kLean) {
-      if (g.G == 16) { if (g.dense) csp_batch_lean_kernel<16, true><<<blocks, threads, sm, s>>>(p); else csp_batch_lean_kernel<16, false><<<blocks, threads, sm, s>>>(p); }
+      if (g.G == 8) { if (g.dense) csp_batch_lean_kernel<8, true><<<blocks, threads, sm, s>>>(p); else csp_batch_lean_kernel<8, false><<<blocks, threads, sm, s>>>(p); }
+      else if (g.G == 16) { if (g.dense) csp_batch_lean_kernel<16, true><<<blocks, threads, sm, s>>>(p); else csp_batch_lean_kernel<16, false><<<blocks, threads, sm, s>>>(p); }
       else { if (g.dense) csp_batch_lean_kernel<32, true><<<blocks, threads, sm, s>>>(p); else csp_batch_lean_kernel<32, false><<<blocks, threads, sm, s>>>(p); }
       return;
     }

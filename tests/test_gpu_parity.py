@@ -255,7 +255,7 @@ def test_cycle_hazard_is_reported(L, O, gpu):
     assert L.compose_frozen_shortest_path(L.MutableFst.compile_string(s), fprod, 1) is None   # reference: OOM -> invalid handle
 
 
-@pytest.mark.parametrize("engine,lanes", [(1, 0), (2, 32), (2, 16), (3, 32), (3, 16)])
+@pytest.mark.parametrize("engine,lanes", [(1, 0), (2, 32), (2, 16), (2, 8), (3, 32), (3, 16), (3, 8), (0, 0)])
 def test_engines_agree(L, O, gpu, engine, lanes):
     """Every kernel choice for byte-string batches (general warp kernel, lean + hash table, lean + dense table;
     32 or 16 lanes per string) must reproduce the oracle bit for bit, in early-exit and exhaustive mode."""
@@ -305,7 +305,7 @@ def test_lean_window_eviction_and_levels(L, O, gpu):
     fprod, forc, _ = frozen_pair(L, O, Spec(n, 0, [0.0 if rng.random() < 0.3 else None for _ in range(n)], arcs))
     strings = [bytes(rng.randint(0, 1) for _ in range(rng.randint(20, 60))) for _ in range(24)]
     try:
-        for engine, lanes in ((2, 32), (3, 32), (3, 16), (2, 16)):
+        for engine, lanes in ((2, 32), (3, 32), (3, 16), (2, 16), (3, 8), (2, 8), (0, 0)):
             for exhaustive in (1, 0):
                 L.configure(engine=engine, lanes_per_string=lanes, exhaustive=exhaustive)
                 res = assert_batch_matches_oracle(L, O, fprod, forc, strings)
