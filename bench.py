@@ -59,7 +59,7 @@ def parse():
     return ap.parse_args()
 
 
-DEFAULT_BATCH = {"epsilon_dense": 4096, "ambiguous": 65536, "plain": 1 << 20}
+DEFAULT_BATCH = {"epsilon_dense": 9472, "ambiguous": 65536, "plain": 1 << 20}   # eps-dense: 64 strings per SM in flight
 
 
 def input_string(workload: str, length: int, branches: int) -> bytes:
@@ -143,8 +143,19 @@ def run_reference(args):
 def workload_config(args, batch, state_bytes):
     return {"workload": f"{SCENARIO[args.workload]} len={args.len} transducer_len={args.transducer_len} branches={args.branches}",
             "batch_per_gpu_per_step": batch, "literal_batch": 1000000,
-            "cache": f"inputs+search state >> L2 (per-step search state ~{state_bytes / 2**30:.1f} GiB in HBM); no L2 flush needed",
-            "lanes_per_string": args.lanes or "auto", "exhaustive": args.exhaustive}
+            "cache": (f"per-step search state ~{state_bytes / 2**30:.1f} GiB in HBM >> 126 MB L2, rewritten by every string; "
+                      f"no L2 flush needed") if state_bytes > (1 << 30) else
+                     "search state fits L2: a buffer larger than L2 is written between timed steps",
+            "lanes_per_string": args.lanes or "auto", "exhaustive": args.exhaustive, "engine": args.engine or "auto"}
+
+
+def measured_traffic(args):
+    """DRAM bytes per string of the search kernel from the committed ncu capture of this workload (profiles/traffic.json)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return t.get(f"{args.workload}:{args.len}:{args.transducer_len}:{args.branches}")
+    except Exception:
+        return None
 
 
 def main():
@@ -204,18 +215,26 @@ def main():
 
     for _ in range(max(args.warmup, 3)):
         step_device()
+    tuples_per_string = float(d_nt.float().mean().item())
+    state_bytes = tuples_per_string * 24 * min(batch, 9472)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if state_bytes <= (1 << 30) else None
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches, relax, kernel_ms = 0, 0, 0.0
-    ev0.record(stream)
+    elapsed_ms = 0.0
     for _ in range(args.steps):
+        if flush is not None:
+            flush.fill_(1)            # evict L2 between timed steps (outside the timed region)
+            torch.cuda.synchronize()
+        ev0.record(stream)
         c = step_device()
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        elapsed_ms += ev0.elapsed_time(ev1)
         launches += c["launches"]; relax += c["relaxations"]; kernel_ms += c["device_ms"]
-    ev1.record(stream)
     barrier()
-    elapsed_ms = ev0.elapsed_time(ev1)
     sampler.stop_flag.set(); sampler.join(timeout=2)
     # correctness of what was timed: every string must have the reference's path length and total
     st = d_status.cpu().numpy(); poff = d_poff.cpu().numpy()
@@ -224,7 +243,6 @@ def main():
     P1 = int(plens[0])
     assert (plens == P1).all(), "bench: identical strings produced different path lengths"
     path0 = (d_il[:P1].cpu().numpy().astype(np.uint32), d_ol[:P1].cpu().numpy().astype(np.uint32), d_w[:P1].cpu().numpy())
-    tuples_per_string = float(d_nt.float().mean().item())
 
     # ── end to end through the host-buffer C ABI ──
     e2e = None
@@ -272,15 +290,17 @@ def main():
     per_launch_bytes = alg_bytes * batch
     kernel_ms_per_launch = kernel_ms / args.steps
     achieved = per_launch_bytes / (kernel_ms_per_launch / 1e3) / 1e9
+    traffic_ps = measured_traffic(args)
     line = {
         "metric": "strings/sec batched compose_shortest_path", "value": value, "unit": "strings/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, batch, tuples_per_string * 90 * min(batch, 4096)),
+        "config": workload_config(args, batch, state_bytes),
         "composed_arcs_per_sec": value * relax_per_string,
         "work_per_string": {"path_arcs": P1, "tuples_run": tuples_per_string, "relax_run": relax_per_string},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "csp_batch_kernel",
+                     "traffic": (traffic_ps * batch if traffic_ps else None), "peak_source": peak_src,
+                     "kernel": "csp_batch_lean_kernel" if not args.engine or args.engine >= 2 else "csp_batch_warp_kernel",
                      "alg_bytes_per_string": alg_bytes, "kernel_ms_per_launch": kernel_ms_per_launch},
         "gpu_launches": launches,
         "clocks": sampler.summary(),
