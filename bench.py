@@ -253,13 +253,15 @@ def main():
         barrier()
         t0 = time.perf_counter()
         d2h = 0
+        e2e_dev_ms = 0.0
         for _ in range(args.steps):
             r = L.compose_frozen_shortest_path_batch(fst, hb, ho)
+            e2e_dev_ms += r.device_ms
             d2h = (r.status.nbytes + r.path_offsets.nbytes + r.ilabels.nbytes + r.olabels.nbytes + r.weights.nbytes +
                    r.final_weights.nbytes + r.n_tuples.nbytes + r.out_offsets.nbytes + r.out_bytes.nbytes)
         torch.cuda.synchronize()
         e2e_ms = (time.perf_counter() - t0) * 1e3
-        e2e = {"ms": e2e_ms, "h2d": int(hb.nbytes + ho.nbytes), "d2h": int(d2h)}
+        e2e = {"ms": e2e_ms, "h2d": int(hb.nbytes + ho.nbytes), "d2h": int(d2h), "dev_ms": e2e_dev_ms}
 
     # ── max over ranks ──
     if dist is not None:
@@ -307,7 +309,8 @@ def main():
     }
     if e2e:
         line["e2e"] = {"value": total_strings / (e2e["ms"] / 1e3), "unit": "strings/s", "h2d_bytes_per_step": e2e["h2d"],
-                       "d2h_bytes_per_step": e2e["d2h"]}
+                       "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": e2e["ms"] / args.steps,
+                       "device_ms_per_step": e2e["dev_ms"] / args.steps}
     if not args.no_cpu_baseline:
         import oracle   # checker + CPU baseline leg only
         f = oracle.Frozen.generate(WORKLOADS[args.workload], args.transducer_len, args.branches)

@@ -124,6 +124,26 @@ template <int G> struct LgG { static constexpr int v = G == 32 ? 5 : (G == 16 ? 
 #define LEAN_L1(c, G) ((c).sm + 128 + (G))
 #define LEAN_COLD(p, c, G) ((c).sm + 128 + (G) + (p).n1)
 
+// Collectives of the hot path.  HOT = true: executed by ALL 32 lanes of the warp with the full mask (one
+// VOTE/SHFL instruction, uniform mask), each group extracting its own lanes; every lane of the warp must
+// reach every HOT collective of an iteration (groups that have nothing to do pass `false`).  HOT = false:
+// the group's own member mask — valid inside code only one group executes (cold paths), but the compiler
+// serialises a warp instruction per distinct mask (measured: ~12 instructions per vote).
+template <int G, bool HOT>
+__device__ __forceinline__ unsigned lean_ballot(const Group<G>& g, bool pred) {
+  if (HOT && G < 32) return (__ballot_sync(0xFFFFFFFFu, pred) >> g.base) & Group<G>::kBits;
+  return g.ballot(pred);
+}
+template <int G, bool HOT, class T>
+__device__ __forceinline__ T lean_shfl(const Group<G>& g, T v, int src) {
+  if (HOT && G < 32) return __shfl_sync(0xFFFFFFFFu, v, (int)g.base + src);
+  return g.shfl(v, src);
+}
+template <int G, bool HOT>
+__device__ __forceinline__ void lean_sync(const Group<G>& g) {
+  if (HOT && G < 32) __syncwarp(); else g.sync();
+}
+
 // Hot per-string state (registers).
 struct LeanState {
   uint32_t n_tuples;
@@ -163,13 +183,18 @@ __device__ __forceinline__ void lean_keyof_load(const SearchParams& p, const Lea
 }
 
 // ── table access ──
+// Dense index, filter-major: ((2P + filter) * S + state).  The match targets of one expansion (filter 0,
+// neighbouring states) are then contiguous 16-byte records instead of every other one.
+__device__ __forceinline__ uint32_t lean_dense_pos(const SearchParams& p, uint32_t P, uint32_t SF) {
+  return (2u * P + (SF & 1u)) * (p.dense_stride >> 1) + (SF >> 1);
+}
 // Find the record of key (P, SF): position and contents; id == kNone <=> not present (hash: `pos` is then
 // the empty slot that ended the probe — pass it to lean_claim before storing).
 template <bool DENSE>
 __device__ __forceinline__ void lean_lookup(const SearchParams& p, const LeanCtx& c, uint32_t P, uint32_t SF, uint32_t& pos, double& dist,
                                             uint32_t& id, uint32_t& prev) {
   if (DENSE) {
-    pos = P * p.dense_stride + SF;
+    pos = lean_dense_pos(p, P, SF);
     const uint4 v = *reinterpret_cast<const uint4*>(c.base + (uint64_t)pos * 16);
     dist = __hiloint2double((int)v.y, (int)v.x); id = v.z; prev = v.w;
   } else {
@@ -225,8 +250,8 @@ __device__ __forceinline__ double lean_dist_of_id(const SearchParams& p, const L
 }
 
 // ── ready set ──
-// Insert ids (collective over the group; one atomic OR per inserting lane).
-template <int G>
+// Insert ids (collective; one atomic OR per inserting lane).
+template <int G, bool HOT>
 __device__ __forceinline__ void lean_ready_insert(const SearchParams& p, const Group<G>& g, const LeanCtx& c, LeanState& st, bool active,
                                                   uint32_t id) {
   bool low = false;
@@ -241,8 +266,8 @@ __device__ __forceinline__ void lean_ready_insert(const SearchParams& p, const G
       low = st.wline != kNone && line < st.wline;
     }
   }
-  if (g.any(low)) st.low_pending = true;
-  g.sync();
+  if (lean_ballot<G, HOT>(g, low)) st.low_pending = true;   // the vote also orders the atomics before the next window read
+  lean_sync<G, HOT>(g);
 }
 // Write the window back (it holds ids above a newly inserted smaller one).
 template <int G>
@@ -455,7 +480,7 @@ __device__ __forceinline__ bool lean_advance_level(const SearchParams& p, const 
           k = (unsigned long long)__double_as_longlong(lean_dist_of_id<DENSE>(p, c, id));
           valid = k > old_last && bucket_of(k, old_last) == b0;
         }
-        lean_ready_insert<G>(p, g, c, st, valid && k == m, id);
+        lean_ready_insert<G, false>(p, g, c, st, valid && k == m, id);
         const bool tb = valid && k != m;
         if (g.any(tb)) lean_bucket_push<G>(p, g, c, st, tb, id, tb ? bucket_of(k, m) : 1u);
       }
@@ -471,19 +496,19 @@ __device__ __forceinline__ bool lean_advance_level(const SearchParams& p, const 
 // device_types.cuh `sarc`); `n_cand` = all arcs of the expansion (the reference's relax calls).
 // `first`: lanes that precede the other lanes in the reference's expansion order (match arcs
 // :182-202 before input-epsilon arcs :254-278); only used to number newly discovered tuples.
-template <int G, bool DENSE>
+// HOT: see lean_ballot — every lane of the warp calls, groups without work pass active = false.
+template <int G, bool DENSE, bool HOT>
 __device__ __forceinline__ void lean_relax(const SearchParams& p, const Group<G>& g, const LeanCtx& c, LeanState& st, uint32_t cur_id,
                                            uint32_t n_cand, bool active, uint32_t P, uint32_t SF, double wmin, unsigned first) {
-  if (n_cand == 0) return;
   st.relax_calls += n_cand;
   uint32_t pos = 0, old_id = 0, old_prev = kNone; double old_dist = d_inf();
   if (active) lean_lookup<DENSE>(p, c, P, SF, pos, old_dist, old_id, old_prev);
   // smallest new distance over the parallel arcs (fl(c + w) is monotone in w)
   const double nd = __longlong_as_double((long long)st.last) + wmin;
   const bool is_new = active && old_id == kNone;
-  const unsigned newmask = g.ballot(is_new);
+  const unsigned newmask = lean_ballot<G, HOT>(g, is_new);
   const uint32_t n_new = __popc(newmask);
-  if (st.n_tuples + n_new > p.tuple_cap) { st.overflow = true; return; }
+  if (st.n_tuples + n_new > p.tuple_cap) { st.overflow = true; active = false; }   // nothing was written yet
   bool lowered = false;
   uint32_t my_id = old_id;
   if (active) {
@@ -499,13 +524,13 @@ __device__ __forceinline__ void lean_relax(const SearchParams& p, const Group<G>
     const bool take = lowered || (nd == old_dist && (old_prev == kNone || cur_id < old_prev)); // :115-126
     if (take) lean_store<DENSE>(c, pos, P, SF, nd, my_id, cur_id);
   }
-  st.n_tuples += n_new;
+  if (!st.overflow) st.n_tuples += n_new;
   // queue: ready set if at the current level, else future set
   const unsigned long long k = (unsigned long long)__double_as_longlong(nd);
-  lean_ready_insert<G>(p, g, c, st, lowered && k == st.last, my_id);
+  lean_ready_insert<G, HOT>(p, g, c, st, lowered && k == st.last, my_id);
   const bool to_future = lowered && k != st.last;
   if (to_future && k < st.future_min) st.future_min = k;
-  if (st.sorted) {
+  if (st.sorted) {   // cold: only this group is in here
     if (g.any(to_future)) lean_bucket_push<G>(p, g, c, st, to_future, my_id, to_future ? bucket_of(k, st.last) : 1u);
   }
 }
@@ -555,31 +580,40 @@ __device__ __forceinline__ void lean_begin(const SearchParams& p, const Group<G>
   g.sync();
 }
 
-// One step of a string: pop the smallest ready id and expand it, or (rarely) switch the window / advance
-// the level.  False: the search is over (queue empty, early stop, or an overflow).
+// One step: pop the smallest ready id and expand it, or (rarely) switch the window / advance the level.
+// Called by ALL lanes of the warp in every iteration in which any of its groups is running (`running` =
+// this lane's group is); the hot collectives are warp-wide, the rare paths are group-local branches.
+// False: this group's search is over (queue empty, early stop, or an overflow).
 template <int G, bool DENSE>
-__device__ __forceinline__ bool lean_step(const SearchParams& p, const Group<G>& g, const LeanCtx& c, LeanState& st, const LhsBytes& lhs) {
-  if (st.overflow || st.heap_overflow) return false;
-  // ── pop the smallest ready id (:159-163; the set only holds unsettled tuples at the level distance) ──
-  if (st.low_pending) { lean_window_evict<G>(p, g, c, st); st.low_pending = false; }
-  const uint32_t w = LEAN_WIN(c)[g.lane];
-  const unsigned bal = g.ballot(w != 0);
-  if (bal == 0) {
-    if (lean_window_next<G, DENSE>(p, g, c, st)) return true;
-    return lean_advance_level<G, DENSE>(p, g, c, st);
-  }
+__device__ __forceinline__ bool lean_step(const SearchParams& p, const Group<G>& g, const LeanCtx& c, LeanState& st, const LhsBytes& lhs,
+                                          bool running) {
+  constexpr bool HOT = true;
   const DevFstView& F = p.fst;
-  const int src = __ffs(bal) - 1;
-  const uint32_t ww = g.shfl(w, src);
-  const uint32_t cur_id = ((st.wline * G + src) << 5) + (__ffs(ww) - 1);
-  if ((int)g.lane == src) LEAN_WIN(c)[src] = ww & (ww - 1);
-  g.sync();
-  uint32_t s1, sf;
-  lean_keyof_load<DENSE>(p, c, cur_id, s1, sf);
+  bool live = running && !(st.overflow || st.heap_overflow);
+  bool over = running && !live;
+  // ── pop the smallest ready id (:159-163; the set only holds unsettled tuples at the level distance) ──
+  if (live && st.low_pending) { lean_window_evict<G>(p, g, c, st); st.low_pending = false; }
+  const uint32_t w = live ? LEAN_WIN(c)[g.lane] : 0u;
+  const unsigned bal = lean_ballot<G, HOT>(g, w != 0);
+  if (live && bal == 0) {   // rare: next window line, or next distance level; the pop happens in the next iteration
+    if (!lean_window_next<G, DENSE>(p, g, c, st)) {
+      if (!lean_advance_level<G, DENSE>(p, g, c, st)) over = true;
+    }
+    live = false;
+  }
+  const int src = live ? __ffs(bal) - 1 : 0;
+  const uint32_t ww = lean_shfl<G, HOT>(g, w, src);
+  uint32_t cur_id = 0, s1 = 0, sf = 0;
+  if (live) {
+    cur_id = ((st.wline * G + src) << 5) + (__ffs(ww) - 1);
+    if ((int)g.lane == src) LEAN_WIN(c)[src] = ww & (ww - 1);
+  }
+  lean_sync<G, HOT>(g);
+  if (live) lean_keyof_load<DENSE>(p, c, cur_id, s1, sf);
   const uint32_t s2 = sf >> 1;
 
   // final check (:165-179): only the last state of the string acceptor is final, weight One
-  if (s1 == lhs.len) {
+  if (live && s1 == lhs.len) {
     const double fw2 = F.final_w[s2];
     if (!d_isinf(fw2)) {
       uint32_t* cold = LEAN_COLD(p, c, G);
@@ -600,41 +634,53 @@ __device__ __forceinline__ bool lean_step(const SearchParams& p, const Group<G>&
     }
   }
   // ── expansion (:182-202 match arcs, then :254-278 input-epsilon arcs; filter is 0 or 1 here) ──
-  const uint4 rec = __ldg(&F.state_rec[s2]);   // {arc_begin, eps_end, arc_end}
-  const uint32_t deg = rec.z - rec.x;
-  const uint32_t x = s1 < lhs.len ? (uint32_t)__ldg(lhs.s + s1) + 1u : 0xFFFFFFFEu;
-  if (deg <= (uint32_t)G) {
-    // one lane per arc of the state, in frozen order (epsilon prefix first)
-    const uint32_t arc = rec.x + g.lane;
-    uint4 sa = make_uint4(0xFFFFFFFFu, 0x80000000u, 0, 0);
-    if (g.lane < deg) sa = __ldg(&F.sarc[arc]);
-    const bool is_match = sa.x == x;               // idle lanes hold ilabel 0xFFFFFFFF, x is never that
-    const bool is_eps = arc < rec.y;               // the epsilon prefix [arc_begin, eps_end)
-    const unsigned first = g.ballot(is_match);
-    lean_relax<G, DENSE>(p, g, c, st, cur_id, __popc(first) + (rec.y - rec.x), (is_match || is_eps) && !(sa.y >> 31),
-                         is_match ? s1 + 1u : s1, (sa.y << 1) | (is_match ? 0u : 1u), __hiloint2double((int)sa.w, (int)sa.z), first);
-  } else {
+  // one lane per arc of the state, in frozen order (the ilabel-0 prefix first); idle lanes hold ilabel 0xFFFFFFFF
+  uint4 sa = make_uint4(0xFFFFFFFFu, 0x80000000u, 0, 0);
+  uint4 rec = make_uint4(0, 0, 0, 0);
+  uint32_t x = 0xFFFFFFFDu;
+  bool big = false;
+  if (live) {
+    x = s1 < lhs.len ? (uint32_t)__ldg(lhs.s + s1) + 1u : 0xFFFFFFFDu;
+    if (F.slab_lanes == (uint32_t)G) {
+      sa = __ldg(&F.slab[(uint64_t)s2 * G + g.lane]);
+      big = sa.x == 0xFFFFFFFEu;
+    } else {
+      rec = __ldg(&F.state_rec[s2]);   // {arc_begin, eps_end, arc_end}
+      const uint32_t deg = rec.z - rec.x;
+      big = deg > (uint32_t)G;
+      if (!big && g.lane < deg) sa = __ldg(&F.sarc[rec.x + g.lane]);
+    }
+  }
+  const bool is_match = sa.x == x;                 // x is never 0xFFFFFFFF / 0xFFFFFFFE (labels are byte + 1)
+  const bool is_eps = sa.x == 0u;                  // ilabel 0 only occurs in the epsilon prefix
+  const unsigned first = lean_ballot<G, HOT>(g, is_match);
+  const unsigned candm = lean_ballot<G, HOT>(g, is_match || is_eps);
+  lean_relax<G, DENSE, HOT>(p, g, c, st, cur_id, __popc(candm), (is_match || is_eps) && !(sa.y >> 31), is_match ? s1 + 1u : s1,
+                            (sa.y << 1) | (is_match ? 0u : 1u), __hiloint2double((int)sa.w, (int)sa.z), first);
+  if (live && big) {
+    // a state wider than the group: binary-searched match range, then the epsilon prefix, G arcs per step
+    if (F.slab_lanes == (uint32_t)G) rec = __ldg(&F.state_rec[s2]);
     uint32_t lo = 0, hi = 0;
     if (s1 < lhs.len) equal_range(g, F.ilabel, rec.x, rec.z, x, lo, hi);
     for (uint32_t cb = lo; cb < hi && !st.overflow && !st.heap_overflow; cb += G) {
       const bool cand = cb + g.lane < hi;
-      uint4 sa = make_uint4(0, 0x80000000u, 0, 0);
-      if (cand) sa = __ldg(&F.sarc[cb + g.lane]);
-      lean_relax<G, DENSE>(p, g, c, st, cur_id, min(hi - cb, (uint32_t)G), cand && !(sa.y >> 31), s1 + 1u, sa.y << 1,
-                           __hiloint2double((int)sa.w, (int)sa.z), Group<G>::kBits);
+      uint4 sb = make_uint4(0, 0x80000000u, 0, 0);
+      if (cand) sb = __ldg(&F.sarc[cb + g.lane]);
+      lean_relax<G, DENSE, false>(p, g, c, st, cur_id, min(hi - cb, (uint32_t)G), cand && !(sb.y >> 31), s1 + 1u, sb.y << 1,
+                                  __hiloint2double((int)sb.w, (int)sb.z), Group<G>::kBits);
       g.sync();
     }
     for (uint32_t cb = rec.x; cb < rec.y && !st.overflow && !st.heap_overflow; cb += G) {
       const bool cand = cb + g.lane < rec.y;
-      uint4 sa = make_uint4(0, 0x80000000u, 0, 0);
-      if (cand) sa = __ldg(&F.sarc[cb + g.lane]);
-      lean_relax<G, DENSE>(p, g, c, st, cur_id, min(rec.y - cb, (uint32_t)G), cand && !(sa.y >> 31), s1, (sa.y << 1) | 1u,
-                           __hiloint2double((int)sa.w, (int)sa.z), Group<G>::kBits);
+      uint4 sb = make_uint4(0, 0x80000000u, 0, 0);
+      if (cand) sb = __ldg(&F.sarc[cb + g.lane]);
+      lean_relax<G, DENSE, false>(p, g, c, st, cur_id, min(rec.y - cb, (uint32_t)G), cand && !(sb.y >> 31), s1, (sb.y << 1) | 1u,
+                                  __hiloint2double((int)sb.w, (int)sb.z), Group<G>::kBits);
       g.sync();
     }
   }
   if (st.relax_calls >= 0x80000000u) { st.relax_hi += st.relax_calls; st.relax_calls = 0; }
-  return true;
+  return !over;
 }
 
 // End of a string: back-track, emit the reversed path into the pool, restore the arena invariants.
@@ -703,7 +749,7 @@ __device__ __forceinline__ int32_t lean_finish(const SearchParams& p, const Grou
       for (uint32_t i = g.lane; i < n; i += G) {
         uint32_t P, SF;
         lean_keyof_load<true>(p, c, i, P, SF);
-        *reinterpret_cast<uint4*>(c.base + (uint64_t)(P * p.dense_stride + SF) * 16) = make_uint4(~0u, ~0u, ~0u, ~0u);
+        *reinterpret_cast<uint4*>(c.base + (uint64_t)lean_dense_pos(p, P, SF) * 16) = make_uint4(~0u, ~0u, ~0u, ~0u);
       }
     } else {
       uint4* t = reinterpret_cast<uint4*>(c.base);
@@ -752,18 +798,17 @@ __global__ void __launch_bounds__(128, FSTB_LEAN_MINBLOCKS) csp_batch_lean_kerne
   enum { kFetch = 0, kRun = 1, kFinish = 2, kDone = 3 };
   uint32_t phase = kFetch, idx = 0;
   LeanState st;
+  st.n_tuples = 0; st.wline = kNone; st.relax_calls = 0; st.last = 0; st.future_min = ~0ull; st.relax_hi = 0;
+  st.low_pending = false; st.overflow = false; st.heap_overflow = false; st.sorted = false;
   LhsBytes lhs; lhs.s = nullptr; lhs.len = 0;
   unsigned long long relax_total = 0, tuple_total = 0;
   for (;;) {
     if (G < 32) {
-      __syncwarp();
       if (__all_sync(0xFFFFFFFFu, phase == kDone)) break;
     } else if (phase == kDone) {
       break;
     }
-    if (phase == kRun) {
-      if (!lean_step<G, DENSE>(p, g, c, st, lhs)) phase = kFinish;
-    } else if (phase == kFetch) {
+    if (phase == kFetch) {
       uint32_t item = 0;
       if (g.lane == 0) item = atomicAdd(p.queue_head, 1u);
       item = g.shfl(item, 0);
@@ -779,7 +824,15 @@ __global__ void __launch_bounds__(128, FSTB_LEAN_MINBLOCKS) csp_batch_lean_kerne
           phase = kRun;
         }
       }
-    } else if (phase == kFinish) {
+    }
+    // the step is warp-uniform: every lane enters it whenever a group of the warp is running
+    const bool anyrun = G < 32 ? __any_sync(0xFFFFFFFFu, phase == kRun) : phase == kRun;
+    if (anyrun) {
+      const bool running = phase == kRun;
+      const bool cont = lean_step<G, DENSE>(p, g, c, st, lhs, running);
+      if (running && !cont) phase = kFinish;
+    }
+    if (phase == kFinish) {
       uint32_t plen; uint64_t poff; double fw;
       const int32_t status = lean_finish<G, DENSE>(p, g, c, st, lhs, &plen, &poff, &fw);
       if (g.lane == 0) {

@@ -28,6 +28,11 @@ struct DevFstView {
   const uint32_t* ilabel;
   const uint4* payload;
   const uint4* sarc;
+  // optional fixed-stride copy of sarc: state s owns slab[s * slab_lanes .. +slab_lanes), unused lanes hold
+  // ilabel 0xFFFFFFFF; a state wider than slab_lanes holds the marker ilabel 0xFFFFFFFE (use the CSR arrays).
+  // Saves the state_rec hop of the per-pop dependent load chain.  slab_lanes == 0: not built.
+  const uint4* slab;
+  uint32_t slab_lanes, pad0;
 };
 
 // General (non-linear) left operand as CSR in STORED arc order

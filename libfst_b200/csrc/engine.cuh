@@ -45,6 +45,7 @@ struct DeviceFst {
   int device = -1;
   DevFstView view{};
   void* block = nullptr;   // one allocation holding all arrays
+  void* slab_block = nullptr;   // fixed-stride search records (lean kernel), may be null
   size_t bytes = 0;
   bool serial = false;     // negative weights: literal sequential relax
   bool lean_ok = false;    // all arc weights finite and >= 0: the lean batched kernel applies
@@ -129,6 +130,23 @@ inline cudaError_t upload_fst(const HostFrozen& f, int device, DeviceFst** out) 
     for (uint32_t s = 0; s < S; s++) { le8 += st[s].num_arcs <= 8; le16 += st[s].num_arcs <= 16; }
     d->lean_lanes = (uint64_t)le8 * 10 >= (uint64_t)S * 9 ? 8 : ((uint64_t)le16 * 10 >= (uint64_t)S * 9 ? 16 : 32);
   }
+  d->view.slab = nullptr; d->view.slab_lanes = 0; d->view.pad0 = 0;
+  const uint32_t GL = d->lean_lanes;
+  if (lean_ok && (uint64_t)S * GL * 16 <= (64ull << 20)) {
+    // fixed-stride copy of the search records: one load per lane per pop without the state_rec hop
+    std::vector<uint4> slab((size_t)S * GL, make_uint4(0xFFFFFFFFu, 0x80000000u, 0, 0));
+    for (uint32_t s = 0; s < S; s++) {
+      const uint32_t b = st[s].arc_offset, n = st[s].num_arcs;
+      if (n <= GL) { for (uint32_t k = 0; k < n; k++) slab[(size_t)s * GL + k] = sa[b + k]; }
+      else { for (uint32_t k = 0; k < GL; k++) slab[(size_t)s * GL + k] = make_uint4(0xFFFFFFFEu, 0x80000000u, 0, 0); }
+    }
+    if (cudaMalloc(&d->slab_block, slab.size() * 16) == cudaSuccess &&
+        cudaMemcpy(d->slab_block, slab.data(), slab.size() * 16, cudaMemcpyHostToDevice) == cudaSuccess) {
+      d->view.slab = static_cast<const uint4*>(d->slab_block); d->view.slab_lanes = GL;
+    } else {
+      cudaGetLastError(); cudaFree(d->slab_block); d->slab_block = nullptr;
+    }
+  }
   *out = d;
   return cudaSuccess;
 }
@@ -137,6 +155,7 @@ inline void free_device_fst(DeviceFst* d) {
   int cur = 0; cudaGetDevice(&cur);
   if (cur != d->device) cudaSetDevice(d->device);
   cudaFree(d->block);
+  cudaFree(d->slab_block);
   if (cur != d->device) cudaSetDevice(cur);
   delete d;
 }
