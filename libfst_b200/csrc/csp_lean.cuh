@@ -148,10 +148,9 @@ __device__ __forceinline__ void lean_sync(const Group<G>& g) {
 struct LeanState {
   uint32_t n_tuples;
   uint32_t wline;                // line held in the window, kNone = none
-  uint32_t relax_calls;
   unsigned long long last;       // bit pattern of the current level distance
   unsigned long long future_min; // per lane: smallest distance pushed beyond the current level
-  unsigned long long relax_hi;   // relax calls beyond 31 bits (flushed rarely)
+  unsigned long long relax_calls;
   bool low_pending;              // a ready id below the window was inserted
   bool overflow;                 // tuple capacity exhausted -> retry with a larger arena
   bool heap_overflow;            // radix-heap pool exhausted -> retry with a deeper pool
@@ -183,10 +182,11 @@ __device__ __forceinline__ void lean_keyof_load(const SearchParams& p, const Lea
 }
 
 // ── table access ──
-// Dense index, filter-major: ((2P + filter) * S + state).  The match targets of one expansion (filter 0,
-// neighbouring states) are then contiguous 16-byte records instead of every other one.
+// Dense index: P * 2S + ((state << 1) | filter) — the two filter variants of a (position, state) pair share a
+// sector.  (A filter-major index, which makes the match targets of one expansion contiguous, was measured:
+// L1 hit rate 55 % -> 43 %, DRAM reads x2.8; the variants are touched close together in time.)
 __device__ __forceinline__ uint32_t lean_dense_pos(const SearchParams& p, uint32_t P, uint32_t SF) {
-  return (2u * P + (SF & 1u)) * (p.dense_stride >> 1) + (SF >> 1);
+  return P * p.dense_stride + SF;
 }
 // Find the record of key (P, SF): position and contents; id == kNone <=> not present (hash: `pos` is then
 // the empty slot that ended the probe — pass it to lean_claim before storing).
@@ -564,7 +564,7 @@ __device__ inline bool lean_recover_arc(const DevFstView& F, const LhsBytes& lhs
 // Precondition (invariant between strings): table untouched-state, ready bitmap, window and summary zero.
 template <int G, bool DENSE>
 __device__ __forceinline__ void lean_begin(const SearchParams& p, const Group<G>& g, const LeanCtx& c, LeanState& st) {
-  st.n_tuples = 1; st.wline = 0; st.relax_calls = 0; st.last = 0; st.future_min = ~0ull; st.relax_hi = 0;
+  st.n_tuples = 1; st.wline = 0; st.relax_calls = 0; st.last = 0; st.future_min = ~0ull;
   st.low_pending = false; st.overflow = false; st.heap_overflow = false; st.sorted = false;
   uint32_t* cold = LEAN_COLD(p, c, G);
   if (g.lane == 0) {
@@ -584,7 +584,7 @@ __device__ __forceinline__ void lean_begin(const SearchParams& p, const Group<G>
 // Called by ALL lanes of the warp in every iteration in which any of its groups is running (`running` =
 // this lane's group is); the hot collectives are warp-wide, the rare paths are group-local branches.
 // False: this group's search is over (queue empty, early stop, or an overflow).
-template <int G, bool DENSE>
+template <int G, bool DENSE, bool SLAB>
 __device__ __forceinline__ bool lean_step(const SearchParams& p, const Group<G>& g, const LeanCtx& c, LeanState& st, const LhsBytes& lhs,
                                           bool running) {
   constexpr bool HOT = true;
@@ -605,11 +605,14 @@ __device__ __forceinline__ bool lean_step(const SearchParams& p, const Group<G>&
   const uint32_t ww = lean_shfl<G, HOT>(g, w, src);
   uint32_t cur_id = 0, s1 = 0, sf = 0;
   if (live) {
-    cur_id = ((st.wline * G + src) << 5) + (__ffs(ww) - 1);
-    if ((int)g.lane == src) LEAN_WIN(c)[src] = ww & (ww - 1);
+    const uint32_t bit = __ffs(ww) - 1;
+    cur_id = ((st.wline * G + src) << 5) + bit;
+    // clear the popped bit atomically: commutes with the atomic ORs of this iteration's inserts (other bits of
+    // the same word), so no barrier is needed in between; the vote + barrier of lean_ready_insert orders all of
+    // them before the next iteration reads the window
+    if ((int)g.lane == src) atomicAnd(&LEAN_WIN(c)[src], ~(1u << bit));
+    lean_keyof_load<DENSE>(p, c, cur_id, s1, sf);
   }
-  lean_sync<G, HOT>(g);
-  if (live) lean_keyof_load<DENSE>(p, c, cur_id, s1, sf);
   const uint32_t s2 = sf >> 1;
 
   // final check (:165-179): only the last state of the string acceptor is final, weight One
@@ -641,7 +644,7 @@ __device__ __forceinline__ bool lean_step(const SearchParams& p, const Group<G>&
   bool big = false;
   if (live) {
     x = s1 < lhs.len ? (uint32_t)__ldg(lhs.s + s1) + 1u : 0xFFFFFFFDu;
-    if (F.slab_lanes == (uint32_t)G) {
+    if (SLAB) {
       sa = __ldg(&F.slab[(uint64_t)s2 * G + g.lane]);
       big = sa.x == 0xFFFFFFFEu;
     } else {
@@ -659,7 +662,7 @@ __device__ __forceinline__ bool lean_step(const SearchParams& p, const Group<G>&
                             (sa.y << 1) | (is_match ? 0u : 1u), __hiloint2double((int)sa.w, (int)sa.z), first);
   if (live && big) {
     // a state wider than the group: binary-searched match range, then the epsilon prefix, G arcs per step
-    if (F.slab_lanes == (uint32_t)G) rec = __ldg(&F.state_rec[s2]);
+    if (SLAB) rec = __ldg(&F.state_rec[s2]);
     uint32_t lo = 0, hi = 0;
     if (s1 < lhs.len) equal_range(g, F.ilabel, rec.x, rec.z, x, lo, hi);
     for (uint32_t cb = lo; cb < hi && !st.overflow && !st.heap_overflow; cb += G) {
@@ -679,7 +682,6 @@ __device__ __forceinline__ bool lean_step(const SearchParams& p, const Group<G>&
       g.sync();
     }
   }
-  if (st.relax_calls >= 0x80000000u) { st.relax_hi += st.relax_calls; st.relax_calls = 0; }
   return !over;
 }
 
@@ -784,7 +786,7 @@ __device__ __forceinline__ int32_t lean_finish(const SearchParams& p, const Grou
 // Persistent batch kernel.  One loop; an iteration is one step of this group's string (fetch the next
 // string / one pop / finish), with a warp-wide reconvergence at the top so that the 16-lane groups of a
 // warp stay in lockstep.
-template <int G, bool DENSE>
+template <int G, bool DENSE, bool SLAB>
 __global__ void __launch_bounds__(128, FSTB_LEAN_MINBLOCKS) csp_batch_lean_kernel(const __grid_constant__ SearchParams p) {
   extern __shared__ __align__(16) uint32_t smem_all[];
   const Group<G> g;
@@ -798,16 +800,11 @@ __global__ void __launch_bounds__(128, FSTB_LEAN_MINBLOCKS) csp_batch_lean_kerne
   enum { kFetch = 0, kRun = 1, kFinish = 2, kDone = 3 };
   uint32_t phase = kFetch, idx = 0;
   LeanState st;
-  st.n_tuples = 0; st.wline = kNone; st.relax_calls = 0; st.last = 0; st.future_min = ~0ull; st.relax_hi = 0;
+  st.n_tuples = 0; st.wline = kNone; st.relax_calls = 0; st.last = 0; st.future_min = ~0ull;
   st.low_pending = false; st.overflow = false; st.heap_overflow = false; st.sorted = false;
   LhsBytes lhs; lhs.s = nullptr; lhs.len = 0;
   unsigned long long relax_total = 0, tuple_total = 0;
   for (;;) {
-    if (G < 32) {
-      if (__all_sync(0xFFFFFFFFu, phase == kDone)) break;
-    } else if (phase == kDone) {
-      break;
-    }
     if (phase == kFetch) {
       uint32_t item = 0;
       if (g.lane == 0) item = atomicAdd(p.queue_head, 1u);
@@ -827,9 +824,11 @@ __global__ void __launch_bounds__(128, FSTB_LEAN_MINBLOCKS) csp_batch_lean_kerne
     }
     // the step is warp-uniform: every lane enters it whenever a group of the warp is running
     const bool anyrun = G < 32 ? __any_sync(0xFFFFFFFFu, phase == kRun) : phase == kRun;
-    if (anyrun) {
+    if (!anyrun) {   // nobody runs: either everybody is done, or somebody finishes/fetches below
+      if (G < 32 ? __all_sync(0xFFFFFFFFu, phase == kDone) : phase == kDone) break;
+    } else {
       const bool running = phase == kRun;
-      const bool cont = lean_step<G, DENSE>(p, g, c, st, lhs, running);
+      const bool cont = lean_step<G, DENSE, SLAB>(p, g, c, st, lhs, running);
       if (running && !cont) phase = kFinish;
     }
     if (phase == kFinish) {
@@ -838,7 +837,7 @@ __global__ void __launch_bounds__(128, FSTB_LEAN_MINBLOCKS) csp_batch_lean_kerne
       if (g.lane == 0) {
         p.status[idx] = status; p.path_len[idx] = plen; p.pool_off[idx] = poff; p.final_w[idx] = fw; p.n_tuples[idx] = st.n_tuples;
       }
-      relax_total += st.relax_hi + st.relax_calls; tuple_total += st.n_tuples;
+      relax_total += st.relax_calls; tuple_total += st.n_tuples;
       phase = kFetch;
     }
   }

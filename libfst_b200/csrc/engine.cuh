@@ -492,11 +492,11 @@ class Engine {
   enum { kSerial = 0, kWarp = 1, kLean = 2 };
   // Arena geometry of one pass: which kernel, and every capacity that shapes the arena.
   struct Geom {
-    int kind = kWarp; uint32_t G = 32; bool dense = false; uint64_t tab_entries = 0;
+    int kind = kWarp; uint32_t G = 32; bool dense = false, slab = false; uint64_t tab_entries = 0;
     uint32_t hash_cap = 0, tuple_cap = 0, heap_cap = 0, bag_cap = 0, smem_per_group = 0; uint64_t stride = 0;
     uint64_t off_l0 = 0, tab_bytes = 0, l0_bytes = 0;
     bool same(const Geom& o) const {
-      return kind == o.kind && G == o.G && dense == o.dense && tab_entries == o.tab_entries && hash_cap == o.hash_cap &&
+      return kind == o.kind && G == o.G && dense == o.dense && slab == o.slab && tab_entries == o.tab_entries && hash_cap == o.hash_cap &&
              tuple_cap == o.tuple_cap && heap_cap == o.heap_cap && bag_cap == o.bag_cap && stride == o.stride;
     }
   };
@@ -528,6 +528,7 @@ class Engine {
     }
     g->kind = kLean;
     g->G = (cfg.lanes_per_string == 8 || cfg.lanes_per_string == 16 || cfg.lanes_per_string == 32) ? cfg.lanes_per_string : fst->lean_lanes;
+    g->slab = fst->view.slab_lanes == g->G;
     const uint64_t E = (uint64_t)(max_len + 1) * fst->view.num_states * 2;
     const bool dense_ok = E < 0xFFFFFF00ull && E * 16 <= kDenseLimitBytes;
     // dense pays when the search touches a good part of the (position x state) grid; a small search keeps its
@@ -561,13 +562,17 @@ class Engine {
     return 8;
   }
 
+  template <int G>
+  static const void* lean_kernel_ptr_g(const Geom& g) {
+    if (g.dense) return g.slab ? (const void*)csp_batch_lean_kernel<G, true, true> : (const void*)csp_batch_lean_kernel<G, true, false>;
+    return g.slab ? (const void*)csp_batch_lean_kernel<G, false, true> : (const void*)csp_batch_lean_kernel<G, false, false>;
+  }
+  static const void* lean_kernel_ptr(const Geom& g) {
+    return g.G == 8 ? lean_kernel_ptr_g<8>(g) : (g.G == 16 ? lean_kernel_ptr_g<16>(g) : lean_kernel_ptr_g<32>(g));
+  }
   static const void* kernel_ptr(const Geom& g) {
     if (g.kind == kWarp) return (const void*)csp_batch_warp_kernel;
-    if (g.kind == kLean) {
-      if (g.G == 8) return g.dense ? (const void*)csp_batch_lean_kernel<8, true> : (const void*)csp_batch_lean_kernel<8, false>;
-      if (g.G == 16) return g.dense ? (const void*)csp_batch_lean_kernel<16, true> : (const void*)csp_batch_lean_kernel<16, false>;
-      return g.dense ? (const void*)csp_batch_lean_kernel<32, true> : (const void*)csp_batch_lean_kernel<32, false>;
-    }
+    if (g.kind == kLean) return lean_kernel_ptr(g);
     switch (g.G) { case 32: return (const void*)csp_batch_kernel<32, true>; case 16: return (const void*)csp_batch_kernel<16, true>;
                    case 8: return (const void*)csp_batch_kernel<8, true>; default: return (const void*)csp_batch_kernel<4, true>; }
   }
@@ -583,9 +588,8 @@ class Engine {
     const size_t sm = (size_t)(threads / g.G) * g.smem_per_group;
     if (g.kind == kWarp) { csp_batch_warp_kernel<<<blocks, threads, sm, s>>>(p); return; }
     if (g.kind == kLean) {
-      if (g.G == 8) { if (g.dense) csp_batch_lean_kernel<8, true><<<blocks, threads, sm, s>>>(p); else csp_batch_lean_kernel<8, false><<<blocks, threads, sm, s>>>(p); }
-      else if (g.G == 16) { if (g.dense) csp_batch_lean_kernel<16, true><<<blocks, threads, sm, s>>>(p); else csp_batch_lean_kernel<16, false><<<blocks, threads, sm, s>>>(p); }
-      else { if (g.dense) csp_batch_lean_kernel<32, true><<<blocks, threads, sm, s>>>(p); else csp_batch_lean_kernel<32, false><<<blocks, threads, sm, s>>>(p); }
+      void* args[] = {const_cast<SearchParams*>(&p)};
+      cudaLaunchKernel(lean_kernel_ptr(g), dim3(blocks), dim3(threads), args, sm, s);
       return;
     }
     switch (g.G) { case 32: csp_batch_kernel<32, true><<<blocks, threads, 0, s>>>(p); break; case 16: csp_batch_kernel<16, true><<<blocks, threads, 0, s>>>(p); break;
