@@ -488,7 +488,9 @@ FstError fst_compose_frozen_shortest_path_batch(FstHandle b, const uint8_t* byte
     cudaMemcpyAsync(d_offsets, rel.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, stream);
     err = en->run_batch(img, d_bytes, d_offsets, n, (uint32_t)max_len, d_status, d_poff, d_il, d_ol, d_w, d_fin, d_nt, path_cap, d_ooff, d_obytes, path_cap, stream, &bc);
     if (err != cudaSuccess) { free_dev(); return err == cudaErrorMemoryAllocation ? FST_OOM : FST_INVALID_STATE; }
-    if (bc.path_required > path_cap && attempt < 4) { path_cap = bc.path_required * 2; free_dev(); continue; }
+    // the flat path arrays were too small (the pool itself may have been large enough from an earlier call)
+    const uint64_t need = std::max<uint64_t>(bc.path_required, bc.path_total);
+    if (need > path_cap && attempt < 4) { path_cap = need + need / 4 + 1024; free_dev(); continue; }
     break;
   }
   t_last = bc;

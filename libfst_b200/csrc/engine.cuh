@@ -580,8 +580,15 @@ class Engine {
     int bps = 0;
     const void* fn = kernel_ptr(g);
     const size_t sm = (size_t)g.smem_per_group * (128 / g.G);
-    if (sm > 40 * 1024) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, 128, sm) != cudaSuccess || bps <= 0) bps = 1;
+    if (sm > 40 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      if (e != cudaSuccess) { std::fprintf(stderr, "[libfst_b200] cudaFuncSetAttribute(smem %zu): %s\n", sm, cudaGetErrorString(e)); cudaGetLastError(); }
+    }
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, 128, sm);
+    if (e != cudaSuccess || bps <= 0) {
+      if (e != cudaSuccess) { std::fprintf(stderr, "[libfst_b200] occupancy query (kind %d G %u smem %zu): %s\n", g.kind, g.G, sm, cudaGetErrorString(e)); cudaGetLastError(); }
+      bps = 1;
+    }
     return (uint32_t)bps * (uint32_t)sm_count * (128 / g.G);
   }
   static void launch_search(const Geom& g, uint32_t blocks, uint32_t threads, const SearchParams& p, cudaStream_t s) {

@@ -65,3 +65,93 @@ def input_string(workload: str, length: int, branches: int) -> bytes:
     if workload == "plain":
         return bytes(i % max(1, branches) for i in range(length))
     return bytes(length)
+
+
+# ── config 4: synthetic WeText-style tagger (not defined by the reference) ──
+_ALNUM = b"abcdefghijklmnopqrstuvwxyz0123456789"
+
+
+def wetext_arrays(K: int = 110000, seed: int = 20261018):
+    """Generator of BASELINE config 4 as plain arrays: (n_states, src, ilabel, olabel, weight, nextstate, sources);
+    start state 0, the only final state is 0 (weight 0).  `sources` are the dictionary keys.
+
+    state 0: start, final 0, 256 identity self-loops (c+1 : c+1 / 1.0 = rewrite.zig IDENTITY_PENALTY);
+    an open insertion chain 0 -e:'t'-> -e:'a'-> -e:'g'-> -e:'{'-> trie root (weights 0);
+    K entries src -> dst (src U[2,8], dst U[0,10] chars over [a-z0-9], weight U{0..8}/8, every fifth entry re-uses
+    an earlier src); src goes into a shared input trie (ch+1 : 0 / 0); from the word-end node an epsilon-input
+    chain emits dst (first arc carries the weight), then (0:0) to a shared close state (carrying the weight if
+    dst is empty), close -e:'}'-> -e:e-> state 0.
+    """
+    rng = np.random.default_rng(seed)
+    src_a, il_a, ol_a, w_a, nx_a = [], [], [], [], []
+
+    def arc(s, il, ol, w, n):
+        src_a.append(s); il_a.append(il); ol_a.append(ol); w_a.append(w); nx_a.append(n)
+
+    n_states = 1
+    for c in range(256):
+        arc(0, c + 1, c + 1, 1.0, 0)
+    prev = 0
+    for ch in b"tag{":
+        arc(prev, 0, ch + 1, 0.0, n_states); prev = n_states; n_states += 1
+    root = prev
+    close = n_states; n_states += 1
+    after = n_states; n_states += 1
+    arc(close, 0, ord("}") + 1, 0.0, after)
+    arc(after, 0, 0, 0.0, 0)
+    trie = {}          # (node, byte) -> node
+    sources = []
+    lens_s = rng.integers(2, 9, K); lens_d = rng.integers(0, 11, K); ws = rng.integers(0, 9, K) / 8.0
+    for k in range(K):
+        if k % 5 == 4 and sources:
+            s = sources[int(rng.integers(0, len(sources)))]
+        else:
+            s = bytes(_ALNUM[i] for i in rng.integers(0, 36, int(lens_s[k])))
+        sources.append(s)
+        d = bytes(_ALNUM[i] for i in rng.integers(0, 36, int(lens_d[k])))
+        node = root
+        for ch in s:
+            nxt = trie.get((node, ch))
+            if nxt is None:
+                nxt = n_states; n_states += 1
+                trie[(node, ch)] = nxt
+                arc(node, ch + 1, 0, 0.0, nxt)
+            node = nxt
+        w = float(ws[k])
+        cur = node
+        for j, ch in enumerate(d):
+            arc(cur, 0, ch + 1, w if j == 0 else 0.0, n_states); cur = n_states; n_states += 1
+        arc(cur, 0, 0, w if len(d) == 0 else 0.0, close)
+    return (n_states, np.array(src_a, np.uint32), np.array(il_a, np.uint32), np.array(ol_a, np.uint32), np.array(w_a, np.float64),
+            np.array(nx_a, np.uint32), sources)
+
+
+def wetext_style(K: int = 110000, seed: int = 20261018):
+    """The config-4 transducer built through the product C ABI: (MutableFst, sources)."""
+    n_states, src, il, ol, w, nxt, sources = wetext_arrays(K, seed)
+    m = MutableFst()
+    m.add_states(n_states)
+    m.set_start(0)
+    m.set_finals(np.array([0], np.uint32), np.zeros(1))
+    rc = m.add_arcs(src, il, ol, w, nxt)
+    assert rc == 0, rc
+    return m, sources
+
+
+def wetext_strings(sources, n: int, seed: int = 1, lo: int = 11, hi: int = 251):
+    """n input strings: length L ~ U[lo,hi]; 70 % concatenated dictionary sources until length >= L, 30 % uniform
+    printable bytes."""
+    rng = np.random.default_rng(seed)
+    out = []
+    Ls = rng.integers(lo, hi + 1, n); kinds = rng.random(n) < 0.7
+    for i in range(n):
+        L = int(Ls[i])
+        if kinds[i]:
+            parts, tot = [], 0
+            while tot < L:
+                s = sources[int(rng.integers(0, len(sources)))]
+                parts.append(s); tot += len(s)
+            out.append(b"".join(parts))
+        else:
+            out.append(bytes(rng.integers(32, 127, L).astype(np.uint8)))
+    return out

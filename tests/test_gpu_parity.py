@@ -313,3 +313,30 @@ def test_lean_window_eviction_and_levels(L, O, gpu):
                     assert max(res.n_tuples) > 1100
     finally:
         L.configure()
+
+
+def test_wetext_style_config4(L, O, gpu):
+    """BASELINE config 4 at reduced scale: trie-shaped tagger with epsilon chains, fractional weights (many distance
+    levels), one 257-arc state; every kernel choice against the oracle."""
+    import os
+    import tempfile
+    from libfst_b200 import synth
+    m, sources = synth.wetext_style(K=3000)
+    fprod = m.freeze()
+    with tempfile.NamedTemporaryFile(suffix=".fst", delete=False) as t:
+        path = t.name
+    try:
+        assert fprod.save(path) == 0
+        forc = O.Frozen.from_bytes(open(path, "rb").read())
+    finally:
+        os.unlink(path)
+    strings = synth.wetext_strings(sources, 160, seed=3, lo=0, hi=80)
+    try:
+        for engine, lanes in ((0, 0), (2, 8), (2, 16), (2, 32), (1, 0)):
+            L.configure(engine=engine, lanes_per_string=lanes)
+            res = assert_batch_matches_oracle(L, O, fprod, forc, strings)
+            assert (res.status == L.PATH).all()
+        L.configure(exhaustive=1)
+        assert_batch_matches_oracle(L, O, fprod, forc, strings[:40])
+    finally:
+        L.configure()
