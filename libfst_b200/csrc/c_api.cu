@@ -144,6 +144,47 @@ struct PinGuard {   // unpin on scope exit (src/c-api.zig:777-781)
   }
 };
 
+struct BatchResultImpl {
+  FstB200BatchResult pub;
+  void* pinned = nullptr;   // one pinned allocation backing all arrays
+  size_t pinned_bytes = 0;
+};
+
+// Pinned result buffers are recycled: page-locking 16 MB per call is milliseconds of driver work.
+static std::mutex g_pin_mu;
+static std::vector<std::pair<void*, size_t>> g_pin_free;
+static void* pinned_alloc(size_t bytes, size_t* got) {
+  {
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    int best = -1;
+    for (int i = 0; i < (int)g_pin_free.size(); i++)
+      if (g_pin_free[i].second >= bytes && (best < 0 || g_pin_free[i].second < g_pin_free[best].second)) best = i;
+    if (best >= 0) {
+      void* p = g_pin_free[best].first; *got = g_pin_free[best].second;
+      g_pin_free.erase(g_pin_free.begin() + best);
+      return p;
+    }
+  }
+  void* p = nullptr;
+  const size_t want = bytes + bytes / 8 + 4096;
+  if (cudaMallocHost(&p, want) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  *got = want;
+  return p;
+}
+static void pinned_release(void* p, size_t bytes) {
+  if (!p) return;
+  {
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    if (g_pin_free.size() < 4) { g_pin_free.emplace_back(p, bytes); return; }
+  }
+  cudaFreeHost(p);
+}
+static void pinned_drain() {
+  std::lock_guard<std::mutex> lk(g_pin_mu);
+  for (auto& e : g_pin_free) cudaFreeHost(e.first);
+  g_pin_free.clear();
+}
+
 }  // namespace
 
 extern "C" {
@@ -420,15 +461,11 @@ void fst_teardown(void) {
     cudaError_t err;
     Engine* en = Engine::for_current_device(&err);
     if (en) { std::lock_guard<std::mutex> lk(en->mu); en->release_all(); }
+    pinned_drain();
   }
 }
 
 // ── batched entry points ──
-struct BatchResultImpl {
-  FstB200BatchResult pub;
-  void* pinned = nullptr;   // one pinned allocation backing all arrays
-};
-
 static int32_t map_status(int32_t s) {
   switch (s) { case kStPath: return FST_B200_PATH; case kStNoPath: return FST_B200_NO_PATH; case kStCycle: return FST_B200_CYCLE;
                case kStInternal: return FST_B200_INTERNAL; default: return FST_B200_TOO_LARGE; }
@@ -463,27 +500,21 @@ FstError fst_compose_frozen_shortest_path_batch(FstHandle b, const uint8_t* byte
   std::lock_guard<std::mutex> lk(en->mu);
   cudaStream_t stream = 0;
   const uint32_t n = n_strings;
-  // device buffers for this call
+  // device buffers of the call: engine-owned, grow-only (cudaMalloc/cudaFree per call cost ~0.3 s per step when
+  // the search workspace holds most of HBM)
   uint8_t* d_bytes = nullptr; uint64_t* d_offsets = nullptr; int32_t* d_status = nullptr; uint64_t* d_poff = nullptr;
   uint32_t *d_il = nullptr, *d_ol = nullptr, *d_nt = nullptr; double *d_w = nullptr, *d_fin = nullptr;
   uint64_t* d_ooff = nullptr; uint8_t* d_obytes = nullptr;
   std::vector<uint64_t> rel(n + 1);
   for (uint32_t i = 0; i <= n; i++) rel[i] = offsets[i] - offsets[0];
   uint64_t path_cap = 2 * nbytes + 16ull * n + 1024;
-  auto free_dev = [&]() {
-    cudaFree(d_bytes); cudaFree(d_offsets); cudaFree(d_status); cudaFree(d_poff); cudaFree(d_il); cudaFree(d_ol); cudaFree(d_nt);
-    cudaFree(d_w); cudaFree(d_fin); cudaFree(d_ooff); cudaFree(d_obytes);
-    d_bytes = nullptr; d_offsets = nullptr; d_status = nullptr; d_poff = nullptr; d_il = d_ol = d_nt = nullptr; d_w = d_fin = nullptr; d_ooff = nullptr; d_obytes = nullptr;
-  };
+  auto free_dev = [&]() {};
   BatchCounters bc;
   for (int attempt = 0;; attempt++) {
-    bool ok = cudaMalloc(&d_bytes, nbytes + 16) == cudaSuccess && cudaMalloc(&d_offsets, (size_t)(n + 1) * 8) == cudaSuccess &&
-              cudaMalloc(&d_status, (size_t)n * 4 + 16) == cudaSuccess && cudaMalloc(&d_poff, (size_t)(n + 1) * 8) == cudaSuccess &&
-              cudaMalloc(&d_il, path_cap * 4) == cudaSuccess && cudaMalloc(&d_ol, path_cap * 4) == cudaSuccess &&
-              cudaMalloc(&d_w, path_cap * 8) == cudaSuccess && cudaMalloc(&d_fin, (size_t)n * 8 + 16) == cudaSuccess &&
-              cudaMalloc(&d_nt, (size_t)n * 4 + 16) == cudaSuccess && cudaMalloc(&d_ooff, (size_t)(n + 1) * 8) == cudaSuccess &&
-              cudaMalloc(&d_obytes, path_cap + 16) == cudaSuccess;
-    if (!ok) { cudaGetLastError(); free_dev(); return FST_OOM; }
+    if (en->ensure_io(n, nbytes, path_cap) != cudaSuccess) { cudaGetLastError(); return FST_OOM; }
+    const Engine::IoBuffers& io = en->io();
+    d_bytes = io.bytes; d_offsets = io.offsets; d_status = io.status; d_poff = io.path_offsets; d_il = io.il; d_ol = io.ol; d_w = io.w;
+    d_fin = io.final_w; d_nt = io.n_tuples; d_ooff = io.out_offsets; d_obytes = io.out_bytes;
     if (nbytes) cudaMemcpyAsync(d_bytes, bytes + offsets[0], nbytes, cudaMemcpyHostToDevice, stream);
     cudaMemcpyAsync(d_offsets, rel.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, stream);
     err = en->run_batch(img, d_bytes, d_offsets, n, (uint32_t)max_len, d_status, d_poff, d_il, d_ol, d_w, d_fin, d_nt, path_cap, d_ooff, d_obytes, path_cap, stream, &bc);
@@ -503,7 +534,8 @@ FstError fst_compose_frozen_shortest_path_batch(FstHandle b, const uint8_t* byte
          o_w = o_ol + al(total * 4), o_fin = o_w + al(total * 8), o_nt = o_fin + al((size_t)n * 8), o_ooff = o_nt + al((size_t)n * 4),
          o_ob = o_ooff + al((size_t)(n + 1) * 8), bytes_total = o_ob + al(out_total) + 64;
   auto* r = new (std::nothrow) BatchResultImpl();
-  if (!r || cudaMallocHost(&r->pinned, bytes_total) != cudaSuccess) { delete r; free_dev(); return FST_OOM; }
+  if (r) r->pinned = pinned_alloc(bytes_total, &r->pinned_bytes);
+  if (!r || !r->pinned) { delete r; free_dev(); return FST_OOM; }
   uint8_t* hb = static_cast<uint8_t*>(r->pinned);
   if (n) {
     cudaMemcpyAsync(hb + o_status, d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, stream);
@@ -520,7 +552,7 @@ FstError fst_compose_frozen_shortest_path_batch(FstHandle b, const uint8_t* byte
   if (out_total) cudaMemcpyAsync(hb + o_ob, d_obytes, out_total, cudaMemcpyDeviceToHost, stream);
   err = cudaStreamSynchronize(stream);
   free_dev();
-  if (err != cudaSuccess) { cudaFreeHost(r->pinned); delete r; return FST_INVALID_STATE; }
+  if (err != cudaSuccess) { pinned_release(r->pinned, r->pinned_bytes); delete r; return FST_INVALID_STATE; }
   int32_t* hs = reinterpret_cast<int32_t*>(hb + o_status);
   for (uint32_t i = 0; i < n; i++) hs[i] = map_status(hs[i]);
   r->pub.n_strings = n;
@@ -545,7 +577,7 @@ FstError fst_compose_frozen_shortest_path_batch(FstHandle b, const uint8_t* byte
 void fst_b200_batch_free(FstB200BatchResult* r) {
   if (!r) return;
   auto* impl = reinterpret_cast<BatchResultImpl*>(r);   // pub is the first member
-  cudaFreeHost(impl->pinned);
+  pinned_release(impl->pinned, impl->pinned_bytes);
   delete impl;
 }
 

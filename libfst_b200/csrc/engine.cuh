@@ -466,7 +466,46 @@ class Engine {
     }
   }
 
+  // Device-side input/output buffers of the host-buffer batch entry (grow-only).
+  struct IoBuffers {
+    uint8_t* bytes = nullptr; uint64_t* offsets = nullptr; int32_t* status = nullptr; uint64_t* path_offsets = nullptr;
+    uint32_t *il = nullptr, *ol = nullptr, *n_tuples = nullptr; double *w = nullptr, *final_w = nullptr;
+    uint64_t* out_offsets = nullptr; uint8_t* out_bytes = nullptr;
+    uint64_t cap_n = 0, cap_bytes = 0, cap_path = 0;
+  };
+  const IoBuffers& io() const { return io_; }
+  cudaError_t ensure_io(uint32_t n, uint64_t nbytes, uint64_t path_cap) {
+    if (n > io_.cap_n) {
+      cudaFree(io_.offsets); cudaFree(io_.status); cudaFree(io_.path_offsets); cudaFree(io_.final_w); cudaFree(io_.n_tuples); cudaFree(io_.out_offsets);
+      io_.offsets = nullptr; io_.status = nullptr; io_.path_offsets = nullptr; io_.final_w = nullptr; io_.n_tuples = nullptr; io_.out_offsets = nullptr;
+      io_.cap_n = 0;
+      const uint64_t m = (uint64_t)n + n / 8 + 16;
+      FSTB_CUDA(cudaMalloc(&io_.offsets, (m + 1) * 8)); FSTB_CUDA(cudaMalloc(&io_.status, m * 4 + 16));
+      FSTB_CUDA(cudaMalloc(&io_.path_offsets, (m + 1) * 8)); FSTB_CUDA(cudaMalloc(&io_.final_w, m * 8 + 16));
+      FSTB_CUDA(cudaMalloc(&io_.n_tuples, m * 4 + 16)); FSTB_CUDA(cudaMalloc(&io_.out_offsets, (m + 1) * 8));
+      io_.cap_n = m;
+    }
+    if (nbytes > io_.cap_bytes) {
+      cudaFree(io_.bytes); io_.bytes = nullptr; io_.cap_bytes = 0;
+      const uint64_t m = nbytes + nbytes / 8 + 256;
+      FSTB_CUDA(cudaMalloc(&io_.bytes, m + 16));
+      io_.cap_bytes = m;
+    }
+    if (path_cap > io_.cap_path) {
+      cudaFree(io_.il); cudaFree(io_.ol); cudaFree(io_.w); cudaFree(io_.out_bytes);
+      io_.il = io_.ol = nullptr; io_.w = nullptr; io_.out_bytes = nullptr; io_.cap_path = 0;
+      const uint64_t m = path_cap + path_cap / 8 + 256;
+      FSTB_CUDA(cudaMalloc(&io_.il, m * 4)); FSTB_CUDA(cudaMalloc(&io_.ol, m * 4)); FSTB_CUDA(cudaMalloc(&io_.w, m * 8));
+      FSTB_CUDA(cudaMalloc(&io_.out_bytes, m + 16));
+      io_.cap_path = m;
+    }
+    return cudaSuccess;
+  }
+
   void release_all() {
+    cudaFree(io_.bytes); cudaFree(io_.offsets); cudaFree(io_.status); cudaFree(io_.path_offsets); cudaFree(io_.il); cudaFree(io_.ol);
+    cudaFree(io_.w); cudaFree(io_.final_w); cudaFree(io_.n_tuples); cudaFree(io_.out_offsets); cudaFree(io_.out_bytes);
+    io_ = IoBuffers();
     cudaFree(d_workspace_); d_workspace_ = nullptr; workspace_bytes_ = 0; layout_groups_ = 0; budget_cache_ = 0;
     free_scratch();
   }
@@ -474,6 +513,7 @@ class Engine {
   uint64_t pool_capacity() const { return pool_cap_; }
 
  private:
+  IoBuffers io_;
   void* d_small_ = nullptr; void* h_small_ = nullptr;
   cudaEvent_t ev0_{}, ev1_{};
   // workspace (arenas)
