@@ -191,6 +191,11 @@ typedef struct {
   uint32_t engine;            /* kernel choice for byte-string batches: 0 = auto, 1 = general
                                  warp kernel, 2 = lean kernel + hash table, 3 = lean kernel +
                                  dense (position x state) table; all produce identical output */
+  uint32_t semantics;         /* 0 = lazy: fst_compose_frozen_shortest_path (compose-shortest-path.zig);
+                                 1 = eager: the result of fst_compose_frozen followed by fst_shortest_path
+                                 (compose.zig:29-198 + shortest-path.zig:18-139; other tie-breaks),
+                                 n_tuples = lattice states, total_relax = lattice arcs; batched entry,
+                                 finite non-negative weights only */
 } FstB200Config;
 FstError fst_b200_configure(const FstB200Config* cfg);
 /* Counters of the last batched call on this thread: kernels launched, relaxations. */

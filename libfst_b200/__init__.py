@@ -44,7 +44,7 @@ class DeviceOut(C.Structure):
 
 class Config(C.Structure):
     _fields_ = [("workspace_bytes", C.c_uint64), ("lanes_per_string", C.c_uint32), ("tuples_hint", C.c_uint32),
-                ("exhaustive", C.c_uint32), ("engine", C.c_uint32)]
+                ("exhaustive", C.c_uint32), ("engine", C.c_uint32), ("semantics", C.c_uint32)]
 
 
 EXPORTS = {
@@ -125,8 +125,11 @@ def device_count() -> int:
 ENGINE_AUTO, ENGINE_WARP, ENGINE_LEAN_HASH, ENGINE_LEAN_DENSE = 0, 1, 2, 3
 
 
-def configure(workspace_bytes=0, lanes_per_string=0, tuples_hint=0, exhaustive=0, engine=0):
-    cfg = Config(workspace_bytes, lanes_per_string, tuples_hint, exhaustive, engine)
+LAZY, EAGER = 0, 1
+
+
+def configure(workspace_bytes=0, lanes_per_string=0, tuples_hint=0, exhaustive=0, engine=0, semantics=0):
+    cfg = Config(workspace_bytes, lanes_per_string, tuples_hint, exhaustive, engine, semantics)
     rc = lib().fst_b200_configure(C.byref(cfg))
     if rc != FST_OK:
         raise ValueError(f"fst_b200_configure failed: {rc}")

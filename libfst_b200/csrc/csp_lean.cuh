@@ -50,6 +50,15 @@
 //     capacities) is read from the kernel parameters in the constant bank at the
 //     point of use, and the cold state (radix-heap cursors, best final) lives in
 //     shared memory, so that the hot loop fits 64 registers (8 blocks per SM).
+//   * EAGER SEMANTICS (BASELINE config 5, SearchParams::eager).  The reference's eager pair — compose()
+//     (compose.zig:29-198: lattice states numbered in FIFO discovery order) then shortestPath()
+//     (shortest-path.zig:18-139: ties broken by the smaller predecessor STATE id, first arc in arc order, best
+//     final = smallest (total, state id)) — gives a result that, for non-negative weights, is a function of the
+//     distance field and the FIFO numbering only: back[v] = the smallest-numbered tight predecessor (every
+//     reachable state pops once and relaxes v; a tie is taken iff the popped state's number is smaller, also on
+//     settled targets, :75-78).  So the kernel (1) runs the exact search above for the distances, then (2) a
+//     BFS phase that pops lattice states in FIFO order (numbers them) and gives every target its FIRST tight
+//     relaxer — which is the smallest-numbered one — as back-pointer, (3) back-tracks with the eager rule.
 #pragma once
 #include "csp_kernels.cuh"
 #include "csp_warp.cuh"   // kChunkIds, kNoChunk, kMaxFastTuples, bucket_of
@@ -68,6 +77,7 @@ static_assert(sizeof(DenseEnt) == 16, "DenseEnt");
 struct __align__(32) LeanSlot { unsigned long long key; unsigned long long spare; double dist; uint32_t id; uint32_t prev; };
 static_assert(sizeof(LeanSlot) == 32, "LeanSlot");
 
+constexpr uint32_t kBfsFlag = 0x40000000u;   // record id field: numbered by the BFS phase (ids stay below 2^22)
 constexpr uint32_t kLeanColdWords = 12;   // smem words of cold per-group state (see LeanCold)
 enum LeanCold : uint32_t { kcChunkNext = 0, kcFreeHead = 1, kcOccLo = 2, kcOccHi = 3, kcHaveBest = 4, kcBestId = 5,
                            kcBestFwLo = 6, kcBestFwHi = 7, kcBestTotLo = 8, kcBestTotHi = 9 };
@@ -155,6 +165,7 @@ struct LeanState {
   bool overflow;                 // tuple capacity exhausted -> retry with a larger arena
   bool heap_overflow;            // radix-heap pool exhausted -> retry with a deeper pool
   bool sorted;                   // the radix heap exists (a second level was needed)
+  bool bfs_started;              // the id -> key array holds BFS numbers (a full table reset is needed after an abort)
 };
 
 // Tuple key of the lean path as a (P, SF) pair: P = string position, SF = (transducer state << 1) | filter
@@ -499,12 +510,39 @@ __device__ __forceinline__ bool lean_advance_level(const SearchParams& p, const 
 // HOT: see lean_ballot — every lane of the warp calls, groups without work pass active = false.
 template <int G, bool DENSE, bool HOT>
 __device__ __forceinline__ void lean_relax(const SearchParams& p, const Group<G>& g, const LeanCtx& c, LeanState& st, uint32_t cur_id,
-                                           uint32_t n_cand, bool active, uint32_t P, uint32_t SF, double wmin, unsigned first) {
+                                           uint32_t n_cand, bool active, uint32_t P, uint32_t SF, double wmin, unsigned first,
+                                           bool bfs = false, double bfs_dist = 0.0) {
   st.relax_calls += n_cand;
   uint32_t pos = 0, old_id = 0, old_prev = kNone; double old_dist = d_inf();
   if (active) lean_lookup<DENSE>(p, c, P, SF, pos, old_dist, old_id, old_prev);
   // smallest new distance over the parallel arcs (fl(c + w) is monotone in w)
-  const double nd = __longlong_as_double((long long)st.last) + wmin;
+  const double nd = (bfs ? bfs_dist : __longlong_as_double((long long)st.last)) + wmin;
+  if (bfs) {
+    // BFS phase of the eager semantics: number the target on first touch (compose.zig:77-91), and give it its
+    // first tight relaxer as back-pointer (== the smallest-numbered tight predecessor, shortest-path.zig:75-78)
+    const bool untouched = active && old_id == kNone;
+    const bool fresh = active && (untouched || !(old_id & kBfsFlag));
+    const unsigned newmask = lean_ballot<G, HOT>(g, fresh);
+    const uint32_t n_new = __popc(newmask);
+    if (st.n_tuples + n_new > p.tuple_cap) { st.overflow = true; active = false; }
+    if (active) {
+      const bool tight = !d_isinf(old_dist) && nd == old_dist;   // an undiscovered target (dist +inf) is never tight
+      if (fresh) {
+        const unsigned lt = g.lt_mask();
+        const bool in_first = (first >> g.lane) & 1u;
+        const uint32_t rank = in_first ? __popc(newmask & first & lt) : (__popc(newmask & first) + __popc(newmask & ~first & lt));
+        const uint32_t my_id = st.n_tuples + rank;
+        lean_keyof_store<DENSE>(p, c, my_id, P, SF);
+        if (untouched) pos = lean_claim<DENSE>(p, c, P, SF, pos);
+        lean_store<DENSE>(c, pos, P, SF, untouched ? d_inf() : old_dist, my_id | kBfsFlag, tight ? cur_id : kNone);
+      } else if (old_prev == kNone && tight) {
+        lean_store<DENSE>(c, pos, P, SF, old_dist, old_id, cur_id);
+      }
+    }
+    if (!st.overflow) st.n_tuples += n_new;
+    lean_ready_insert<G, HOT>(p, g, c, st, false, 0u);   // keeps the warp-wide collective sequence of the search step
+    return;
+  }
   const bool is_new = active && old_id == kNone;
   const unsigned newmask = lean_ballot<G, HOT>(g, is_new);
   const uint32_t n_new = __popc(newmask);
@@ -565,7 +603,7 @@ __device__ inline bool lean_recover_arc(const DevFstView& F, const LhsBytes& lhs
 template <int G, bool DENSE>
 __device__ __forceinline__ void lean_begin(const SearchParams& p, const Group<G>& g, const LeanCtx& c, LeanState& st) {
   st.n_tuples = 1; st.wline = 0; st.relax_calls = 0; st.last = 0; st.future_min = ~0ull;
-  st.low_pending = false; st.overflow = false; st.heap_overflow = false; st.sorted = false;
+  st.low_pending = false; st.overflow = false; st.heap_overflow = false; st.sorted = false; st.bfs_started = false;
   uint32_t* cold = LEAN_COLD(p, c, G);
   if (g.lane == 0) {
     const uint32_t SF = p.fst.start << 1;
@@ -584,39 +622,70 @@ __device__ __forceinline__ void lean_begin(const SearchParams& p, const Group<G>
 // Called by ALL lanes of the warp in every iteration in which any of its groups is running (`running` =
 // this lane's group is); the hot collectives are warp-wide, the rare paths are group-local branches.
 // False: this group's search is over (queue empty, early stop, or an overflow).
-template <int G, bool DENSE, bool SLAB>
+// `mode`: 0 = this lane's group is not running, 1 = search step, 2 = BFS step of the eager semantics (pops are
+// the lattice states in FIFO order: st.wline is the cursor).
+template <int G, bool DENSE, bool SLAB, bool EAGER>
 __device__ __forceinline__ bool lean_step(const SearchParams& p, const Group<G>& g, const LeanCtx& c, LeanState& st, const LhsBytes& lhs,
-                                          bool running) {
+                                          uint32_t mode) {
   constexpr bool HOT = true;
   const DevFstView& F = p.fst;
+  const bool running = mode != 0, bfs = EAGER && mode == 2;
   bool live = running && !(st.overflow || st.heap_overflow);
   bool over = running && !live;
   // ── pop the smallest ready id (:159-163; the set only holds unsettled tuples at the level distance) ──
-  if (live && st.low_pending) { lean_window_evict<G>(p, g, c, st); st.low_pending = false; }
-  const uint32_t w = live ? LEAN_WIN(c)[g.lane] : 0u;
+  if (live && !bfs && st.low_pending) { lean_window_evict<G>(p, g, c, st); st.low_pending = false; }
+  const uint32_t w = (live && !bfs) ? LEAN_WIN(c)[g.lane] : 0u;
   const unsigned bal = lean_ballot<G, HOT>(g, w != 0);
-  if (live && bal == 0) {   // rare: next window line, or next distance level; the pop happens in the next iteration
+  if (live && !bfs && bal == 0) {   // rare: next window line, or next distance level; the pop happens in the next iteration
     if (!lean_window_next<G, DENSE>(p, g, c, st)) {
       if (!lean_advance_level<G, DENSE>(p, g, c, st)) over = true;
     }
     live = false;
   }
-  const int src = live ? __ffs(bal) - 1 : 0;
+  if (live && bfs && st.wline >= st.n_tuples) { over = true; live = false; }   // FIFO drained: the lattice is complete
+  const int src = (live && !bfs) ? __ffs(bal) - 1 : 0;
   const uint32_t ww = lean_shfl<G, HOT>(g, w, src);
   uint32_t cur_id = 0, s1 = 0, sf = 0;
+  double bfs_dist = d_inf();
   if (live) {
-    const uint32_t bit = __ffs(ww) - 1;
-    cur_id = ((st.wline * G + src) << 5) + bit;
-    // clear the popped bit atomically: commutes with the atomic ORs of this iteration's inserts (other bits of
-    // the same word), so no barrier is needed in between; the vote + barrier of lean_ready_insert orders all of
-    // them before the next iteration reads the window
-    if ((int)g.lane == src) atomicAnd(&LEAN_WIN(c)[src], ~(1u << bit));
+    if (bfs) {
+      cur_id = st.wline++;
+    } else {
+      const uint32_t bit = __ffs(ww) - 1;
+      cur_id = ((st.wline * G + src) << 5) + bit;
+      // clear the popped bit atomically: commutes with the atomic ORs of this iteration's inserts (other bits of
+      // the same word), so no barrier is needed in between; the vote + barrier of lean_ready_insert orders all of
+      // them before the next iteration reads the window
+      if ((int)g.lane == src) atomicAnd(&LEAN_WIN(c)[src], ~(1u << bit));
+    }
     lean_keyof_load<DENSE>(p, c, cur_id, s1, sf);
+    if (bfs) { uint32_t ps, i2, pr; lean_lookup<DENSE>(p, c, s1, sf, ps, bfs_dist, i2, pr); }
   }
   const uint32_t s2 = sf >> 1;
 
+  // eager final pick (shortest-path.zig:88-104): smallest (total, state number) over reached final states; the BFS
+  // pops in increasing number, so only a strictly smaller total replaces the best
+  if (live && bfs && s1 == lhs.len && !d_isinf(bfs_dist)) {
+    const double fw2 = F.final_w[s2];
+    if (!d_isinf(fw2)) {
+      uint32_t* cold = LEAN_COLD(p, c, G);
+      const double final_w = 0.0 + fw2;
+      const double total = bfs_dist + final_w;
+      const bool have_best = cold[kcHaveBest] != 0;
+      const double best_total = __hiloint2double((int)cold[kcBestTotHi], (int)cold[kcBestTotLo]);
+      g.sync();
+      if (!have_best || total < best_total) {
+        if (g.lane == 0) {
+          cold[kcHaveBest] = 1; cold[kcBestId] = cur_id;
+          cold[kcBestFwLo] = (uint32_t)__double2loint(final_w); cold[kcBestFwHi] = (uint32_t)__double2hiint(final_w);
+          cold[kcBestTotLo] = (uint32_t)__double2loint(total); cold[kcBestTotHi] = (uint32_t)__double2hiint(total);
+        }
+      }
+      g.sync();
+    }
+  }
   // final check (:165-179): only the last state of the string acceptor is final, weight One
-  if (live && s1 == lhs.len) {
+  if (live && !bfs && s1 == lhs.len) {
     const double fw2 = F.final_w[s2];
     if (!d_isinf(fw2)) {
       uint32_t* cold = LEAN_COLD(p, c, G);
@@ -659,7 +728,7 @@ __device__ __forceinline__ bool lean_step(const SearchParams& p, const Group<G>&
   const unsigned first = lean_ballot<G, HOT>(g, is_match);
   const unsigned candm = lean_ballot<G, HOT>(g, is_match || is_eps);
   lean_relax<G, DENSE, HOT>(p, g, c, st, cur_id, __popc(candm), (is_match || is_eps) && !(sa.y >> 31), is_match ? s1 + 1u : s1,
-                            (sa.y << 1) | (is_match ? 0u : 1u), __hiloint2double((int)sa.w, (int)sa.z), first);
+                            (sa.y << 1) | (is_match ? 0u : 1u), __hiloint2double((int)sa.w, (int)sa.z), first, bfs, bfs_dist);
   if (live && big) {
     // a state wider than the group: binary-searched match range, then the epsilon prefix, G arcs per step
     if (SLAB) rec = __ldg(&F.state_rec[s2]);
@@ -670,7 +739,7 @@ __device__ __forceinline__ bool lean_step(const SearchParams& p, const Group<G>&
       uint4 sb = make_uint4(0, 0x80000000u, 0, 0);
       if (cand) sb = __ldg(&F.sarc[cb + g.lane]);
       lean_relax<G, DENSE, false>(p, g, c, st, cur_id, min(hi - cb, (uint32_t)G), cand && !(sb.y >> 31), s1 + 1u, sb.y << 1,
-                                  __hiloint2double((int)sb.w, (int)sb.z), Group<G>::kBits);
+                                  __hiloint2double((int)sb.w, (int)sb.z), Group<G>::kBits, bfs, bfs_dist);
       g.sync();
     }
     for (uint32_t cb = rec.x; cb < rec.y && !st.overflow && !st.heap_overflow; cb += G) {
@@ -678,11 +747,29 @@ __device__ __forceinline__ bool lean_step(const SearchParams& p, const Group<G>&
       uint4 sb = make_uint4(0, 0x80000000u, 0, 0);
       if (cand) sb = __ldg(&F.sarc[cb + g.lane]);
       lean_relax<G, DENSE, false>(p, g, c, st, cur_id, min(rec.y - cb, (uint32_t)G), cand && !(sb.y >> 31), s1, (sb.y << 1) | 1u,
-                                  __hiloint2double((int)sb.w, (int)sb.z), Group<G>::kBits);
+                                  __hiloint2double((int)sb.w, (int)sb.z), Group<G>::kBits, bfs, bfs_dist);
       g.sync();
     }
   }
   return !over;
+}
+
+// Start the BFS phase of the eager semantics after the search: the initial tuple is lattice state 0
+// (compose.zig:57-61); st.wline becomes the FIFO cursor, st.n_tuples the number of states numbered so far.
+template <int G, bool DENSE>
+__device__ __forceinline__ void lean_bfs_begin(const SearchParams& p, const Group<G>& g, const LeanCtx& c, LeanState& st) {
+  uint32_t* cold = LEAN_COLD(p, c, G);
+  g.sync();
+  if (g.lane == 0) {
+    const uint32_t SF = p.fst.start << 1;
+    uint32_t pos, id, prev; double d;
+    lean_lookup<DENSE>(p, c, 0u, SF, pos, d, id, prev);
+    lean_store<DENSE>(c, pos, 0u, SF, 0.0, 0u | kBfsFlag, kNone);
+    lean_keyof_store<DENSE>(p, c, 0u, 0u, SF);
+    cold[kcHaveBest] = 0;
+  }
+  st.n_tuples = 1; st.wline = 0; st.relax_calls = 0; st.bfs_started = true;
+  g.sync();
 }
 
 // End of a string: back-track, emit the reversed path into the pool, restore the arena invariants.
@@ -709,11 +796,17 @@ __device__ __forceinline__ int32_t lean_finish(const SearchParams& p, const Grou
   } else {
     if (g.lane == 0) {                                                // :372-380 back-track (ids only)
       uint32_t cur = best_id;
-      while (cur != 0) {
+      const bool eager = st.bfs_started;
+      while (eager || cur != 0) {
         uint32_t P, SF, pos, id, prev; double d;
         lean_keyof_load<DENSE>(p, c, cur, P, SF);
         lean_lookup<DENSE>(p, c, P, SF, pos, d, id, prev);
-        if (prev == kNone) { status = kStNoPath; break; }             // :375-377
+        if (prev == kNone) {
+          // lazy: a missing back-pointer before the initial tuple -> empty FST (:375-377); eager: the chain ends at
+          // the first state without back-pointer, which must be the start state (shortest-path.zig:113-123)
+          if (!eager || cur != 0) status = kStNoPath;
+          break;
+        }
         if (plen >= st.n_tuples) { status = kStCycle; break; }        // hazard H1 (reference: out of memory)
         if (plen >= scratch_cap) { status = kStRetryHeap; break; }
         scratch[plen++] = cur;
@@ -746,7 +839,12 @@ __device__ __forceinline__ int32_t lean_finish(const SearchParams& p, const Grou
   // Restore the arena invariants for the next string: table untouched-state, bitmaps zero.
   g.sync();
   const uint32_t n = st.n_tuples;
-  if (DENSE) {
+  const bool mixed = st.bfs_started && (st.overflow || st.heap_overflow);   // id -> key array is part search ids, part BFS numbers
+  if (mixed) {
+    uint4* t = reinterpret_cast<uint4*>(c.base);
+    const uint64_t vecs = p.tab_entries * (DENSE ? 1ull : 2ull);
+    for (uint64_t i = g.lane; i < vecs; i += G) t[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+  } else if (DENSE) {
     if ((uint64_t)n * 4 < p.tab_entries) {
       for (uint32_t i = g.lane; i < n; i += G) {
         uint32_t P, SF;
@@ -774,7 +872,7 @@ __device__ __forceinline__ int32_t lean_finish(const SearchParams& p, const Grou
   }
   if (st.overflow || st.heap_overflow) {
     // aborted searches can leave ready bits behind
-    for (uint32_t i = g.lane; i < ((n + 32u * G - 1) / (32u * G)) * G; i += G) LEAN_L0(p, c)[i] = 0;
+    for (uint32_t i = g.lane; i < ((p.tuple_cap + 32u * G - 1) / (32u * G)) * G; i += G) LEAN_L0(p, c)[i] = 0;
     for (uint32_t i = g.lane; i < p.n1; i += G) LEAN_L1(c, G)[i] = 0;
     LEAN_WIN(c)[g.lane] = 0;
   }
@@ -786,7 +884,7 @@ __device__ __forceinline__ int32_t lean_finish(const SearchParams& p, const Grou
 // Persistent batch kernel.  One loop; an iteration is one step of this group's string (fetch the next
 // string / one pop / finish), with a warp-wide reconvergence at the top so that the 16-lane groups of a
 // warp stay in lockstep.
-template <int G, bool DENSE, bool SLAB>
+template <int G, bool DENSE, bool SLAB, bool EAGER>
 __global__ void __launch_bounds__(128, FSTB_LEAN_MINBLOCKS) csp_batch_lean_kernel(const __grid_constant__ SearchParams p) {
   extern __shared__ __align__(16) uint32_t smem_all[];
   const Group<G> g;
@@ -797,11 +895,11 @@ __global__ void __launch_bounds__(128, FSTB_LEAN_MINBLOCKS) csp_batch_lean_kerne
   c.sm = smem_all + (size_t)gib * p.smem_words;
   for (uint32_t i = 128 + g.lane; i < p.smem_words; i += G) c.sm[i] = 0;   // window, summary and cold state start empty
   g.sync();
-  enum { kFetch = 0, kRun = 1, kFinish = 2, kDone = 3 };
+  enum { kFetch = 0, kRun = 1, kFinish = 2, kDone = 3, kBfs = 4 };
   uint32_t phase = kFetch, idx = 0;
   LeanState st;
   st.n_tuples = 0; st.wline = kNone; st.relax_calls = 0; st.last = 0; st.future_min = ~0ull;
-  st.low_pending = false; st.overflow = false; st.heap_overflow = false; st.sorted = false;
+  st.low_pending = false; st.overflow = false; st.heap_overflow = false; st.sorted = false; st.bfs_started = false;
   LhsBytes lhs; lhs.s = nullptr; lhs.len = 0;
   unsigned long long relax_total = 0, tuple_total = 0;
   for (;;) {
@@ -823,13 +921,16 @@ __global__ void __launch_bounds__(128, FSTB_LEAN_MINBLOCKS) csp_batch_lean_kerne
       }
     }
     // the step is warp-uniform: every lane enters it whenever a group of the warp is running
-    const bool anyrun = G < 32 ? __any_sync(0xFFFFFFFFu, phase == kRun) : phase == kRun;
+    const bool stepping = phase == kRun || (EAGER && phase == kBfs);
+    const bool anyrun = G < 32 ? __any_sync(0xFFFFFFFFu, stepping) : stepping;
     if (!anyrun) {   // nobody runs: either everybody is done, or somebody finishes/fetches below
       if (G < 32 ? __all_sync(0xFFFFFFFFu, phase == kDone) : phase == kDone) break;
     } else {
-      const bool running = phase == kRun;
-      const bool cont = lean_step<G, DENSE, SLAB>(p, g, c, st, lhs, running);
-      if (running && !cont) phase = kFinish;
+      const bool cont = lean_step<G, DENSE, SLAB, EAGER>(p, g, c, st, lhs, phase == kRun ? 1u : (phase == kBfs ? 2u : 0u));
+      if (stepping && !cont) {
+        if (EAGER && phase == kRun && !st.overflow && !st.heap_overflow) { lean_bfs_begin<G, DENSE>(p, g, c, st); phase = kBfs; }
+        else phase = kFinish;
+      }
     }
     if (phase == kFinish) {
       uint32_t plen; uint64_t poff; double fw;

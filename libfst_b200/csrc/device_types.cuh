@@ -94,6 +94,7 @@ struct SearchParams {
   uint32_t smem_words;     // shared-memory words per group
   uint32_t dense_stride;   // 2 * S: dense index = p * dense_stride + ((s << 1) | filter)
   uint32_t key_sbits;      // dense: bits of ((s << 1) | filter) in the compact id -> key array
+  uint32_t eager;          // lean path: 1 = eager semantics (compose() then shortestPath(), BASELINE config 5)
   // work queue + counters
   uint32_t* queue_head;
   unsigned long long* pool_cursor;

@@ -37,6 +37,7 @@ struct Config {
   uint32_t tuples_hint = 0;
   uint32_t exhaustive = 0;
   uint32_t engine = 0;       // 0 auto, 1 general warp kernel, 2 lean + hash table, 3 lean + dense table
+  uint32_t semantics = 0;    // 0 lazy (composeShortestPath), 1 eager (compose then shortestPath; lean kernel only)
 };
 inline Config& global_config() { static Config c; return c; }
 
@@ -257,6 +258,10 @@ class Engine {
       bc->passes++;
       Geom gm;
       if (!geometry(cfg, fst, max_len, tuple_cap, heap_mult, &gm)) { too_large(); break; }
+      if (cfg.semantics == 1 && gm.kind != kLean) {
+        std::fprintf(stderr, "[libfst_b200] eager semantics need finite non-negative weights (lean kernel)\n");
+        too_large(); break;
+      }
       const uint32_t max_groups = max_resident_groups(gm);
       const uint32_t want = std::min<uint32_t>(n_items, max_groups);
       const uint64_t ws = workspace_budget(cfg);
@@ -283,6 +288,7 @@ class Engine {
         p.off_keyof = L.off_keyof; p.off_l0 = L.off_l0; p.off_chunks = L.off_chunks;
         p.n1 = L.n1; p.smem_words = L.smem_words; p.dense_stride = fst->view.num_states * 2u;
         p.key_sbits = 1; while ((1u << p.key_sbits) < p.dense_stride) p.key_sbits++;
+        p.eager = cfg.semantics == 1 ? 1u : 0u;
       }
       p.queue_head = d_cnt + 0;
       p.pool_cursor = reinterpret_cast<unsigned long long*>(d_cnt + 2);
@@ -532,7 +538,7 @@ class Engine {
   enum { kSerial = 0, kWarp = 1, kLean = 2 };
   // Arena geometry of one pass: which kernel, and every capacity that shapes the arena.
   struct Geom {
-    int kind = kWarp; uint32_t G = 32; bool dense = false, slab = false; uint64_t tab_entries = 0;
+    int kind = kWarp; uint32_t G = 32; bool dense = false, slab = false, eager = false; uint64_t tab_entries = 0;
     uint32_t hash_cap = 0, tuple_cap = 0, heap_cap = 0, bag_cap = 0, smem_per_group = 0; uint64_t stride = 0;
     uint64_t off_l0 = 0, tab_bytes = 0, l0_bytes = 0;
     bool same(const Geom& o) const {
@@ -569,6 +575,7 @@ class Engine {
     g->kind = kLean;
     g->G = (cfg.lanes_per_string == 8 || cfg.lanes_per_string == 16 || cfg.lanes_per_string == 32) ? cfg.lanes_per_string : fst->lean_lanes;
     g->slab = fst->view.slab_lanes == g->G;
+    g->eager = cfg.semantics == 1;
     const uint64_t E = (uint64_t)(max_len + 1) * fst->view.num_states * 2;
     const bool dense_ok = E < 0xFFFFFF00ull && E * 16 <= kDenseLimitBytes;
     // dense pays when the search touches a good part of the (position x state) grid; a small search keeps its
@@ -602,11 +609,13 @@ class Engine {
     return 8;
   }
 
-  template <int G>
-  static const void* lean_kernel_ptr_g(const Geom& g) {
-    if (g.dense) return g.slab ? (const void*)csp_batch_lean_kernel<G, true, true> : (const void*)csp_batch_lean_kernel<G, true, false>;
-    return g.slab ? (const void*)csp_batch_lean_kernel<G, false, true> : (const void*)csp_batch_lean_kernel<G, false, false>;
+  template <int G, bool EAGER>
+  static const void* lean_kernel_ptr_ge(const Geom& g) {
+    if (g.dense) return g.slab ? (const void*)csp_batch_lean_kernel<G, true, true, EAGER> : (const void*)csp_batch_lean_kernel<G, true, false, EAGER>;
+    return g.slab ? (const void*)csp_batch_lean_kernel<G, false, true, EAGER> : (const void*)csp_batch_lean_kernel<G, false, false, EAGER>;
   }
+  template <int G>
+  static const void* lean_kernel_ptr_g(const Geom& g) { return g.eager ? lean_kernel_ptr_ge<G, true>(g) : lean_kernel_ptr_ge<G, false>(g); }
   static const void* lean_kernel_ptr(const Geom& g) {
     return g.G == 8 ? lean_kernel_ptr_g<8>(g) : (g.G == 16 ? lean_kernel_ptr_g<16>(g) : lean_kernel_ptr_g<32>(g));
   }

@@ -122,3 +122,28 @@ def assert_batch_matches_oracle(L, O, fprod, forc, strings, res=None, check_out=
         if check_out:
             assert res.output(i) == p.output_bytes(), (i, s)
     return res
+
+
+def assert_batch_matches_eager_oracle(L, O, fprod, forc, strings, res=None):
+    """Eager semantics (BASELINE config 5): the product batch (configured with semantics=EAGER) against the oracle's
+    compose() followed by shortestPath() (compose.zig:29-198, shortest-path.zig:18-139), bit-exact."""
+    if res is None:
+        data, offsets = L.pack_strings(strings)
+        res = L.compose_frozen_shortest_path_batch(fprod, data, offsets)
+    for i, s in enumerate(strings):
+        p, lat_states, lat_arcs = O.eager_mutable(O.Mutable.compile_string(s), forc, 1)
+        if p.status == O.STATUS_BACKTRACK_CYCLE:
+            assert res.status[i] == L.CYCLE, (i, s, res.status[i])
+            continue
+        if p.status == O.STATUS_EMPTY:
+            assert res.status[i] == L.NO_PATH, (i, s, res.status[i])
+            continue
+        assert res.status[i] == L.PATH, (i, s, res.status[i], p.status)
+        il, ol, w = res.path(i)
+        assert np.array_equal(il, p.ilabels), (i, s, il, p.ilabels)
+        assert np.array_equal(ol, p.olabels), (i, s, ol, p.olabels)
+        assert np.array_equal(w.view(np.uint64), p.weights.view(np.uint64)), (i, s, w, p.weights)
+        a, b = np.float64(res.final_weights[i]), np.float64(p.final_weight)
+        assert a.view(np.uint64) == b.view(np.uint64), (i, s, a, b)
+        assert res.n_tuples[i] == lat_states, (i, s, res.n_tuples[i], lat_states)   # the whole lattice was numbered
+    return res

@@ -340,3 +340,39 @@ def test_wetext_style_config4(L, O, gpu):
         assert_batch_matches_oracle(L, O, fprod, forc, strings[:40])
     finally:
         L.configure()
+
+
+@pytest.mark.parametrize("engine,lanes", [(0, 0), (2, 32), (3, 16), (2, 8), (3, 8)])
+def test_eager_semantics_config5(L, O, gpu, engine, lanes):
+    """BASELINE config 5 / SURVEY rows a14+a15: the path of compose() followed by shortestPath() (different
+    tie-breaking than the lazy search: lattice states numbered in FIFO order, no label tie-break)."""
+    from common import assert_batch_matches_eager_oracle
+    rng = random.Random(909 + engine)
+    cases = []
+    for case in range(40):
+        spec = random_rhs(rng, real=(case % 4 == 3))
+        fprod, forc, _ = frozen_pair(L, O, spec)
+        cases.append((fprod, forc, [random_string(rng, max_len=8) for _ in range(30)]))
+    for kind, lens in ((2, [0, 1, 11, 33, 96]), (1, [0, 5, 11]), (0, [7, 96])):
+        img = gen_image(O, kind, 4096 if kind != 1 else 512, 12)
+        strings = [bytes(i % 12 for i in range(k)) if kind == 0 else bytes(k) for k in lens]
+        cases.append((L.Fst.from_image(img), O.Frozen.from_bytes(img), strings))
+    differ = 0
+    try:
+        for exhaustive in (0, 1):
+            L.configure(engine=engine, lanes_per_string=lanes, exhaustive=exhaustive, semantics=L.EAGER)
+            for fprod, forc, strings in cases:
+                assert_batch_matches_eager_oracle(L, O, fprod, forc, strings)
+        # the two semantics really differ on some tie-heavy inputs (SURVEY App. C: ~2 %)
+        L.configure(engine=engine, lanes_per_string=lanes, semantics=L.LAZY)
+        for fprod, forc, strings in cases[:40]:
+            data, offsets = L.pack_strings(strings)
+            lazy = L.compose_frozen_shortest_path_batch(fprod, data, offsets)
+            for i, s in enumerate(strings):
+                pe, _, _ = O.eager_mutable(O.Mutable.compile_string(s), forc, 1)
+                if pe.status == O.STATUS_OK and lazy.status[i] == L.PATH:
+                    il, ol, w = lazy.path(i)
+                    differ += not (np.array_equal(il, pe.ilabels) and np.array_equal(ol, pe.olabels))
+    finally:
+        L.configure()
+    assert differ > 0
