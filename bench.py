@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--exhaustive", type=int, default=0)
     ap.add_argument("--dict", type=int, default=110000, help="wetext workload: dictionary entries (110000 ~ 1 M arcs)")
     ap.add_argument("--tuples-hint", type=int, default=0, help="expected tuples per string (0 = adaptive: learnt in warm-up)")
+    ap.add_argument("--semantics", default="lazy", choices=["lazy", "eager"],
+                    help="lazy = fst_compose_frozen_shortest_path (headline); eager = compose then shortest_path (config 5)")
     ap.add_argument("--engine", type=int, default=0, help="0 auto, 1 general warp kernel, 2 lean+hash, 3 lean+dense")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -167,16 +169,17 @@ def run_reference(args):
     f, sources = make_reference_workload(args)
     probe_n = 64 if args.workload == "wetext" else 1
     pdata, poff, _ = workload_strings(args, probe_n, 1, sources)
-    t0 = time.time(); oracle.csp_batch_bytes(f, pdata, poff, n_threads=1); one = max((time.time() - t0) / probe_n, 1e-7)
+    eager = args.semantics == "eager"
+    t0 = time.time(); oracle.csp_batch_bytes(f, pdata, poff, n_threads=1, eager=eager); one = max((time.time() - t0) / probe_n, 1e-7)
     # bounded sample per step: a few seconds of work on all cores
     sample = args.cpu_sample or int(max(cores, min(cores * 4096, cores * max(1.0, 5.0 / one))))
     data, offsets, _ = workload_strings(args, sample, 1, sources)
     R1 = 0.0
     for _ in range(args.warmup):
-        oracle.csp_batch_bytes(f, data, offsets, n_threads=cores)
+        oracle.csp_batch_bytes(f, data, offsets, n_threads=cores, eager=eager)
     secs = 0.0
     for _ in range(args.steps):
-        r = oracle.csp_batch_bytes(f, data, offsets, n_threads=cores)
+        r = oracle.csp_batch_bytes(f, data, offsets, n_threads=cores, eager=eager)
         secs += r["seconds"]; R1 = r["relax_calls"] / sample
     ms = secs / args.steps * 1e3
     v = sample / (ms / 1e3)
@@ -199,7 +202,9 @@ def workload_config(args, batch, state_bytes):
     desc = (f"{SCENARIO[args.workload]} dict={args.dict} len=U[11,251] (70% dictionary words, 30% printable bytes)"
             if args.workload == "wetext" else
             f"{SCENARIO[args.workload]} len={args.len} transducer_len={args.transducer_len} branches={args.branches}")
-    return {"workload": desc,
+    if args.semantics == "eager":
+        desc = desc.replace("compose_frozen_lazy_shortest_path", "compose_frozen") + " + shortest_path (eager lattice, config 5)"
+    return {"workload": desc, "semantics": args.semantics,
             "batch_per_gpu_per_step": batch, "literal_batch": 1000000,
             "cache": (f"per-step search state ~{state_bytes / 2**30:.1f} GiB in HBM >> 126 MB L2, rewritten by every string; "
                       f"no L2 flush needed") if state_bytes > (1 << 30) else
@@ -235,7 +240,8 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L.load()
-    L.configure(lanes_per_string=args.lanes, exhaustive=args.exhaustive, engine=args.engine, tuples_hint=args.tuples_hint)
+    L.configure(lanes_per_string=args.lanes, exhaustive=args.exhaustive, engine=args.engine, tuples_hint=args.tuples_hint,
+                semantics=L.EAGER if args.semantics == "eager" else L.LAZY)
 
     batch = args.batch or DEFAULT_BATCH[args.workload]
     # every rank searches its own `batch` strings (weak scaling); the transducer is replicated per GPU
@@ -379,7 +385,11 @@ def main():
         tr, rr = 0, 0
         for i in range(n_check):
             a, b = int(offsets[i]), int(offsets[i + 1])
-            p1 = oracle.csp_bytes(f, data[a:b].tobytes())
+            if args.semantics == "eager":
+                p1, ls, la = oracle.eager_mutable(oracle.Mutable.compile_string(data[a:b].tobytes()), f, 1)
+                p1.tuples, p1.relax_calls = ls, la
+            else:
+                p1 = oracle.csp_bytes(f, data[a:b].tobytes())
             lo, hi = int(poff[i]), int(poff[i + 1])
             ok = (st[i] == 0) == (p1.status == oracle.STATUS_OK)
             if ok and st[i] == 0:
@@ -390,7 +400,8 @@ def main():
         one = max((time.time() - t0) / n_check, 1e-7)
         line["work_per_string"].update({"tuples_ref": tr / n_check, "relax_ref": rr / n_check, "checked_vs_oracle": n_check})
         sample = args.cpu_sample or int(max(cores, min(batch, cores * 4096, cores * max(1.0, 10.0 / one))))
-        secs = oracle.csp_batch_bytes(f, data[:int(offsets[sample])], offsets[:sample + 1], n_threads=cores)["seconds"]
+        secs = oracle.csp_batch_bytes(f, data[:int(offsets[sample])], offsets[:sample + 1], n_threads=cores,
+                                      eager=args.semantics == "eager")["seconds"]
         line["cpu_baseline"] = {"value": sample / secs, "unit": "strings/s", "cores": cores, "kind": "port",
                                 "sample": f"first {sample} strings of the same batch on {cores} threads ({secs:.1f} s); C++ "
                                           f"restatement of the reference (zig toolchain absent)"}

@@ -166,6 +166,8 @@ struct LeanState {
   bool heap_overflow;            // radix-heap pool exhausted -> retry with a deeper pool
   bool sorted;                   // the radix heap exists (a second level was needed)
   bool bfs_started;              // the id -> key array holds BFS numbers (a full table reset is needed after an abort)
+  bool stuck;                    // safety valve tripped (see the kernel loop)
+  uint32_t occ;                  // eager BFS phase: records in the table = search tuples + tuples first met by the BFS
 };
 
 // Tuple key of the lean path as a (P, SF) pair: P = string position, SF = (transducer state << 1) | filter
@@ -508,45 +510,27 @@ __device__ __forceinline__ bool lean_advance_level(const SearchParams& p, const 
 // `first`: lanes that precede the other lanes in the reference's expansion order (match arcs
 // :182-202 before input-epsilon arcs :254-278); only used to number newly discovered tuples.
 // HOT: see lean_ballot — every lane of the warp calls, groups without work pass active = false.
-template <int G, bool DENSE, bool HOT>
+template <int G, bool DENSE, bool HOT, bool EAGER = true>
 __device__ __forceinline__ void lean_relax(const SearchParams& p, const Group<G>& g, const LeanCtx& c, LeanState& st, uint32_t cur_id,
                                            uint32_t n_cand, bool active, uint32_t P, uint32_t SF, double wmin, unsigned first,
                                            bool bfs = false, double bfs_dist = 0.0) {
+  // NOTE: the search step and the BFS step of the eager semantics share every collective CALL SITE below —
+  // groups of one warp can be in different modes, and a warp-wide collective only matches itself.
   st.relax_calls += n_cand;
   uint32_t pos = 0, old_id = 0, old_prev = kNone; double old_dist = d_inf();
   if (active) lean_lookup<DENSE>(p, c, P, SF, pos, old_dist, old_id, old_prev);
   // smallest new distance over the parallel arcs (fl(c + w) is monotone in w)
   const double nd = (bfs ? bfs_dist : __longlong_as_double((long long)st.last)) + wmin;
-  if (bfs) {
-    // BFS phase of the eager semantics: number the target on first touch (compose.zig:77-91), and give it its
-    // first tight relaxer as back-pointer (== the smallest-numbered tight predecessor, shortest-path.zig:75-78)
-    const bool untouched = active && old_id == kNone;
-    const bool fresh = active && (untouched || !(old_id & kBfsFlag));
-    const unsigned newmask = lean_ballot<G, HOT>(g, fresh);
-    const uint32_t n_new = __popc(newmask);
-    if (st.n_tuples + n_new > p.tuple_cap) { st.overflow = true; active = false; }
-    if (active) {
-      const bool tight = !d_isinf(old_dist) && nd == old_dist;   // an undiscovered target (dist +inf) is never tight
-      if (fresh) {
-        const unsigned lt = g.lt_mask();
-        const bool in_first = (first >> g.lane) & 1u;
-        const uint32_t rank = in_first ? __popc(newmask & first & lt) : (__popc(newmask & first) + __popc(newmask & ~first & lt));
-        const uint32_t my_id = st.n_tuples + rank;
-        lean_keyof_store<DENSE>(p, c, my_id, P, SF);
-        if (untouched) pos = lean_claim<DENSE>(p, c, P, SF, pos);
-        lean_store<DENSE>(c, pos, P, SF, untouched ? d_inf() : old_dist, my_id | kBfsFlag, tight ? cur_id : kNone);
-      } else if (old_prev == kNone && tight) {
-        lean_store<DENSE>(c, pos, P, SF, old_dist, old_id, cur_id);
-      }
-    }
-    if (!st.overflow) st.n_tuples += n_new;
-    lean_ready_insert<G, HOT>(p, g, c, st, false, 0u);   // keeps the warp-wide collective sequence of the search step
-    return;
-  }
-  const bool is_new = active && old_id == kNone;
+  const bool untouched = active && old_id == kNone;
+  // search: a target is new when it has no record; BFS: when it has no BFS number yet (compose.zig:77-91)
+  const bool is_new = bfs ? (active && (untouched || !(old_id & kBfsFlag))) : untouched;
   const unsigned newmask = lean_ballot<G, HOT>(g, is_new);
   const uint32_t n_new = __popc(newmask);
-  if (st.n_tuples + n_new > p.tuple_cap) { st.overflow = true; active = false; }   // nothing was written yet
+  // BFS: the table holds the search's tuples AND the ones the BFS met first, while n_tuples restarts at 1 — bound
+  // the records (occ >= n_tuples), or a hash table sized for tuple_cap fills up and probing never ends
+  uint32_t n_unt = 0;
+  if (EAGER) n_unt = __popc(lean_ballot<G, HOT>(g, bfs && untouched));
+  if ((EAGER && bfs ? st.occ + n_unt : st.n_tuples + n_new) > p.tuple_cap) { st.overflow = true; active = false; }   // nothing was written yet
   bool lowered = false;
   uint32_t my_id = old_id;
   if (active) {
@@ -556,19 +540,27 @@ __device__ __forceinline__ void lean_relax(const SearchParams& p, const Group<G>
       const uint32_t rank = in_first ? __popc(newmask & first & lt) : (__popc(newmask & first) + __popc(newmask & ~first & lt));
       my_id = st.n_tuples + rank;   // discovery order == reference expansion order (:80-87)
       lean_keyof_store<DENSE>(p, c, my_id, P, SF);
-      pos = lean_claim<DENSE>(p, c, P, SF, pos);
+      if (untouched) pos = lean_claim<DENSE>(p, c, P, SF, pos);
     }
-    lowered = is_new || nd < old_dist;                                                         // :109-114, :137-142
-    const bool take = lowered || (nd == old_dist && (old_prev == kNone || cur_id < old_prev)); // :115-126
-    if (take) lean_store<DENSE>(c, pos, P, SF, nd, my_id, cur_id);
+    if (bfs) {
+      // eager semantics: the first tight relaxer in FIFO order is the smallest-numbered tight predecessor
+      // (shortest-path.zig:75-78); a target the search never reached (dist +inf) is never tight
+      const bool tight = !d_isinf(old_dist) && nd == old_dist;
+      if (is_new) lean_store<DENSE>(c, pos, P, SF, untouched ? d_inf() : old_dist, my_id | kBfsFlag, tight ? cur_id : kNone);
+      else if (old_prev == kNone && tight) lean_store<DENSE>(c, pos, P, SF, old_dist, old_id, cur_id);
+    } else {
+      lowered = is_new || nd < old_dist;                                                         // :109-114, :137-142
+      const bool take = lowered || (nd == old_dist && (old_prev == kNone || cur_id < old_prev)); // :115-126
+      if (take) lean_store<DENSE>(c, pos, P, SF, nd, my_id, cur_id);
+    }
   }
-  if (!st.overflow) st.n_tuples += n_new;
-  // queue: ready set if at the current level, else future set
+  if (!st.overflow) { st.n_tuples += n_new; if (EAGER) st.occ += n_unt; }
+  // queue: ready set if at the current level, else future set (the BFS step inserts nothing)
   const unsigned long long k = (unsigned long long)__double_as_longlong(nd);
   lean_ready_insert<G, HOT>(p, g, c, st, lowered && k == st.last, my_id);
   const bool to_future = lowered && k != st.last;
   if (to_future && k < st.future_min) st.future_min = k;
-  if (st.sorted) {   // cold: only this group is in here
+  if (st.sorted && !bfs) {   // cold: only this group is in here
     if (g.any(to_future)) lean_bucket_push<G>(p, g, c, st, to_future, my_id, to_future ? bucket_of(k, st.last) : 1u);
   }
 }
@@ -603,7 +595,7 @@ __device__ inline bool lean_recover_arc(const DevFstView& F, const LhsBytes& lhs
 template <int G, bool DENSE>
 __device__ __forceinline__ void lean_begin(const SearchParams& p, const Group<G>& g, const LeanCtx& c, LeanState& st) {
   st.n_tuples = 1; st.wline = 0; st.relax_calls = 0; st.last = 0; st.future_min = ~0ull;
-  st.low_pending = false; st.overflow = false; st.heap_overflow = false; st.sorted = false; st.bfs_started = false;
+  st.low_pending = false; st.overflow = false; st.heap_overflow = false; st.sorted = false; st.bfs_started = false; st.stuck = false; st.occ = 0;
   uint32_t* cold = LEAN_COLD(p, c, G);
   if (g.lane == 0) {
     const uint32_t SF = p.fst.start << 1;
@@ -727,7 +719,7 @@ __device__ __forceinline__ bool lean_step(const SearchParams& p, const Group<G>&
   const bool is_eps = sa.x == 0u;                  // ilabel 0 only occurs in the epsilon prefix
   const unsigned first = lean_ballot<G, HOT>(g, is_match);
   const unsigned candm = lean_ballot<G, HOT>(g, is_match || is_eps);
-  lean_relax<G, DENSE, HOT>(p, g, c, st, cur_id, __popc(candm), (is_match || is_eps) && !(sa.y >> 31), is_match ? s1 + 1u : s1,
+  lean_relax<G, DENSE, HOT, EAGER>(p, g, c, st, cur_id, __popc(candm), (is_match || is_eps) && !(sa.y >> 31), is_match ? s1 + 1u : s1,
                             (sa.y << 1) | (is_match ? 0u : 1u), __hiloint2double((int)sa.w, (int)sa.z), first, bfs, bfs_dist);
   if (live && big) {
     // a state wider than the group: binary-searched match range, then the epsilon prefix, G arcs per step
@@ -738,7 +730,7 @@ __device__ __forceinline__ bool lean_step(const SearchParams& p, const Group<G>&
       const bool cand = cb + g.lane < hi;
       uint4 sb = make_uint4(0, 0x80000000u, 0, 0);
       if (cand) sb = __ldg(&F.sarc[cb + g.lane]);
-      lean_relax<G, DENSE, false>(p, g, c, st, cur_id, min(hi - cb, (uint32_t)G), cand && !(sb.y >> 31), s1 + 1u, sb.y << 1,
+      lean_relax<G, DENSE, false, EAGER>(p, g, c, st, cur_id, min(hi - cb, (uint32_t)G), cand && !(sb.y >> 31), s1 + 1u, sb.y << 1,
                                   __hiloint2double((int)sb.w, (int)sb.z), Group<G>::kBits, bfs, bfs_dist);
       g.sync();
     }
@@ -746,7 +738,7 @@ __device__ __forceinline__ bool lean_step(const SearchParams& p, const Group<G>&
       const bool cand = cb + g.lane < rec.y;
       uint4 sb = make_uint4(0, 0x80000000u, 0, 0);
       if (cand) sb = __ldg(&F.sarc[cb + g.lane]);
-      lean_relax<G, DENSE, false>(p, g, c, st, cur_id, min(rec.y - cb, (uint32_t)G), cand && !(sb.y >> 31), s1, (sb.y << 1) | 1u,
+      lean_relax<G, DENSE, false, EAGER>(p, g, c, st, cur_id, min(rec.y - cb, (uint32_t)G), cand && !(sb.y >> 31), s1, (sb.y << 1) | 1u,
                                   __hiloint2double((int)sb.w, (int)sb.z), Group<G>::kBits, bfs, bfs_dist);
       g.sync();
     }
@@ -768,6 +760,7 @@ __device__ __forceinline__ void lean_bfs_begin(const SearchParams& p, const Grou
     lean_keyof_store<DENSE>(p, c, 0u, 0u, SF);
     cold[kcHaveBest] = 0;
   }
+  st.occ = st.n_tuples;
   st.n_tuples = 1; st.wline = 0; st.relax_calls = 0; st.bfs_started = true;
   g.sync();
 }
@@ -787,7 +780,9 @@ __device__ __forceinline__ int32_t lean_finish(const SearchParams& p, const Grou
   const bool have_best = cold[kcHaveBest] != 0;
   const uint32_t best_id = cold[kcBestId];
   const double best_fw = __hiloint2double((int)cold[kcBestFwHi], (int)cold[kcBestFwLo]);
-  if (st.overflow) {
+  if (st.stuck) {
+    status = kStInternal;
+  } else if (st.overflow) {
     status = kStRetry;
   } else if (st.heap_overflow) {
     status = kStRetryHeap;
@@ -839,7 +834,8 @@ __device__ __forceinline__ int32_t lean_finish(const SearchParams& p, const Grou
   // Restore the arena invariants for the next string: table untouched-state, bitmaps zero.
   g.sync();
   const uint32_t n = st.n_tuples;
-  const bool mixed = st.bfs_started && (st.overflow || st.heap_overflow);   // id -> key array is part search ids, part BFS numbers
+  const bool aborted = st.overflow || st.heap_overflow || st.stuck;
+  const bool mixed = st.bfs_started && aborted;   // id -> key array is part search ids, part BFS numbers
   if (mixed) {
     uint4* t = reinterpret_cast<uint4*>(c.base);
     const uint64_t vecs = p.tab_entries * (DENSE ? 1ull : 2ull);
@@ -870,7 +866,7 @@ __device__ __forceinline__ int32_t lean_finish(const SearchParams& p, const Grou
     LeanSlot* tab = reinterpret_cast<LeanSlot*>(c.base);
     for (uint32_t i = g.lane; i < n; i += G) tab[slot_tmp[i]].key = kEmptyKey;
   }
-  if (st.overflow || st.heap_overflow) {
+  if (aborted) {
     // aborted searches can leave ready bits behind
     for (uint32_t i = g.lane; i < ((p.tuple_cap + 32u * G - 1) / (32u * G)) * G; i += G) LEAN_L0(p, c)[i] = 0;
     for (uint32_t i = g.lane; i < p.n1; i += G) LEAN_L1(c, G)[i] = 0;
@@ -897,9 +893,10 @@ __global__ void __launch_bounds__(128, FSTB_LEAN_MINBLOCKS) csp_batch_lean_kerne
   g.sync();
   enum { kFetch = 0, kRun = 1, kFinish = 2, kDone = 3, kBfs = 4 };
   uint32_t phase = kFetch, idx = 0;
+  uint32_t steps = 0;   // safety valve: steps of the current string (tuple_cap <= 4 M, so the bound fits 32 bits)
   LeanState st;
   st.n_tuples = 0; st.wline = kNone; st.relax_calls = 0; st.last = 0; st.future_min = ~0ull;
-  st.low_pending = false; st.overflow = false; st.heap_overflow = false; st.sorted = false; st.bfs_started = false;
+  st.low_pending = false; st.overflow = false; st.heap_overflow = false; st.sorted = false; st.bfs_started = false; st.stuck = false; st.occ = 0;
   LhsBytes lhs; lhs.s = nullptr; lhs.len = 0;
   unsigned long long relax_total = 0, tuple_total = 0;
   for (;;) {
@@ -916,7 +913,7 @@ __global__ void __launch_bounds__(128, FSTB_LEAN_MINBLOCKS) csp_batch_lean_kerne
           if (g.lane == 0) { p.status[idx] = kStNoPath; p.path_len[idx] = 0; p.pool_off[idx] = 0; p.final_w[idx] = d_inf(); p.n_tuples[idx] = 0; }
         } else {
           lean_begin<G, DENSE>(p, g, c, st);
-          phase = kRun;
+          phase = kRun; steps = 0;
         }
       }
     }
@@ -926,9 +923,12 @@ __global__ void __launch_bounds__(128, FSTB_LEAN_MINBLOCKS) csp_batch_lean_kerne
     if (!anyrun) {   // nobody runs: either everybody is done, or somebody finishes/fetches below
       if (G < 32 ? __all_sync(0xFFFFFFFFu, phase == kDone) : phase == kDone) break;
     } else {
-      const bool cont = lean_step<G, DENSE, SLAB, EAGER>(p, g, c, st, lhs, phase == kRun ? 1u : (phase == kBfs ? 2u : 0u));
+      bool cont = lean_step<G, DENSE, SLAB, EAGER>(p, g, c, st, lhs, phase == kRun ? 1u : (phase == kBfs ? 2u : 0u));
+      // every step pops a tuple or retires a window line / distance level: more than a few steps per tuple slot
+      // means the engine is not making progress — fail the string (kStInternal) instead of spinning
+      if (stepping && ++steps > 8u * p.tuple_cap + 4096u) { st.stuck = true; cont = false; }
       if (stepping && !cont) {
-        if (EAGER && phase == kRun && !st.overflow && !st.heap_overflow) { lean_bfs_begin<G, DENSE>(p, g, c, st); phase = kBfs; }
+        if (EAGER && phase == kRun && !st.overflow && !st.heap_overflow && !st.stuck) { lean_bfs_begin<G, DENSE>(p, g, c, st); phase = kBfs; }
         else phase = kFinish;
       }
     }

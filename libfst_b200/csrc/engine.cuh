@@ -308,6 +308,9 @@ class Engine {
       FSTB_CUDA(cudaStreamSynchronize(stream));
       const uint32_t* hc = static_cast<const uint32_t*>(h_small_);
       const uint32_t retry = hc[1], heap_retry = hc[9];
+      if (std::getenv("LIBFST_B200_DEBUG"))
+        std::fprintf(stderr, "[libfst_b200] pass %u kind %d G %u dense %d eager %d tuple_cap %u heap_cap %u items %u groups %u retry %u heap_retry %u\n",
+                     pass, gm.kind, gm.G, (int)gm.dense, (int)gm.eager, gm.tuple_cap, gm.heap_cap, n_items, blocks * gpb, retry, heap_retry);
       unsigned long long pool_used; std::memcpy(&pool_used, hc + 2, 8);
       if (retry == 0) break;
       if (pool_used > pool_cap_) {

@@ -80,6 +80,7 @@ def lib():
         "orc_csp_bytes": (None, [vp, pu8, u32, u32, pu32, pu32, pd, C.POINTER(_Info)]),
         "orc_eager_mutable": (None, [vp, vp, u32, u32, pu32, pu32, pd, C.POINTER(_Info), pu64, pu64]),
         "orc_csp_batch_bytes": (dbl, [vp, pu8, pu64, u32, u32, u32, pu32, pu32, pd, pi32, pu32, pd, pd, pu64, pu64]),
+        "orc_eager_batch_bytes": (dbl, [vp, pu8, pu64, u32, u32, u32, pu32, pu32, pd, pi32, pu32, pd, pd, pu64, pu64]),
         "orc_print_string": (C.c_int32, [vp, C.c_int, pu8, u32]),
     }
     for name, (res, args) in sig.items():
@@ -230,8 +231,9 @@ def eager_mutable(lhs: Mutable, fst: Frozen, n: int = 1, cap: int = 1 << 16):
     return _mk_path(info, il, ol, w), ls.value, la.value
 
 
-def csp_batch_bytes(fst: Frozen, data: np.ndarray, offsets: np.ndarray, n_threads: int = 1, cap: int = 0):
-    """Thread-pool batch (CPU baseline).  Returns dict with seconds, per-string arrays, work sums."""
+def csp_batch_bytes(fst: Frozen, data: np.ndarray, offsets: np.ndarray, n_threads: int = 1, cap: int = 0, eager: bool = False):
+    """Thread-pool batch (CPU baseline).  Returns dict with seconds, per-string arrays, work sums.
+    eager=True runs compose() + shortestPath() per string instead of composeShortestPath()."""
     data = np.ascontiguousarray(data, np.uint8)
     if data.size == 0:
         data = np.zeros(1, np.uint8)
@@ -243,7 +245,7 @@ def csp_batch_bytes(fst: Frozen, data: np.ndarray, offsets: np.ndarray, n_thread
     if cap:
         il, ol, w = np.zeros(n * cap, np.uint32), np.zeros(n * cap, np.uint32), np.zeros(n * cap, np.float64)
     st, sr = C.c_uint64(0), C.c_uint64(0)
-    secs = lib().orc_csp_batch_bytes(fst.ptr, _p(data, C.c_uint8), _p(offsets, C.c_uint64), n, n_threads, cap,
+    secs = (lib().orc_eager_batch_bytes if eager else lib().orc_csp_batch_bytes)(fst.ptr, _p(data, C.c_uint8), _p(offsets, C.c_uint64), n, n_threads, cap,
                                      _p(il, C.c_uint32), _p(ol, C.c_uint32), _p(w, C.c_double),
                                      _p(status, C.c_int32), _p(lens, C.c_uint32), _p(finals, C.c_double),
                                      _p(totals, C.c_double), C.byref(st), C.byref(sr))

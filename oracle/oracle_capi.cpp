@@ -107,10 +107,10 @@ void orc_eager_mutable(void* lhs, void* fst, uint32_t n, uint32_t cap, uint32_t*
 // Outputs: per-string status/len/final/total and flat path arrays with a fixed
 // per-string capacity `cap` (arrays may be null to time only).
 // Returns wall seconds of the search region.
-double orc_csp_batch_bytes(void* fst, const uint8_t* bytes, const uint64_t* offsets, uint32_t n_strings,
-                           uint32_t n_threads, uint32_t cap, uint32_t* il, uint32_t* ol, double* w,
-                           int32_t* status, uint32_t* lens, double* finals, double* totals,
-                           uint64_t* sum_tuples, uint64_t* sum_relax) {
+static double batch_bytes_impl(void* fst, const uint8_t* bytes, const uint64_t* offsets, uint32_t n_strings,
+                               uint32_t n_threads, uint32_t cap, uint32_t* il, uint32_t* ol, double* w,
+                               int32_t* status, uint32_t* lens, double* finals, double* totals,
+                               uint64_t* sum_tuples, uint64_t* sum_relax, bool eager) {
   std::atomic<uint32_t> next{0};
   std::atomic<uint64_t> st{0}, sr{0};
   const Fst& f = *(Fst*)fst;
@@ -121,7 +121,14 @@ double orc_csp_batch_bytes(void* fst, const uint8_t* bytes, const uint64_t* offs
       if (i >= n_strings) break;
       MutableFst m = compile_string(bytes + offsets[i], (size_t)(offsets[i + 1] - offsets[i]));
       MutableLhs l{&m};
-      PathResult r = compose_shortest_path(l, f, 1);
+      PathResult r;
+      if (eager) {   // compose (compose.zig) then shortestPath (shortest-path.zig); work = lattice size
+        MutableFst lat = compose(l, f);
+        r = shortest_path(lat, 1);
+        r.stats.tuples = lat.num_states(); r.stats.relax_calls = lat.total_arcs();
+      } else {
+        r = compose_shortest_path(l, f, 1);
+      }
       lt += r.stats.tuples; lr += r.stats.relax_calls;
       if (status) status[i] = (int32_t)r.status;
       if (lens) lens[i] = (uint32_t)r.arcs.size();
@@ -148,6 +155,20 @@ double orc_csp_batch_bytes(void* fst, const uint8_t* bytes, const uint64_t* offs
   if (sum_tuples) *sum_tuples = st.load();
   if (sum_relax) *sum_relax = sr.load();
   return std::chrono::duration<double>(t1 - t0).count();
+}
+
+double orc_csp_batch_bytes(void* fst, const uint8_t* bytes, const uint64_t* offsets, uint32_t n_strings,
+                           uint32_t n_threads, uint32_t cap, uint32_t* il, uint32_t* ol, double* w,
+                           int32_t* status, uint32_t* lens, double* finals, double* totals,
+                           uint64_t* sum_tuples, uint64_t* sum_relax) {
+  return batch_bytes_impl(fst, bytes, offsets, n_strings, n_threads, cap, il, ol, w, status, lens, finals, totals, sum_tuples, sum_relax, false);
+}
+// Same driver for the eager pair (BASELINE config 5).
+double orc_eager_batch_bytes(void* fst, const uint8_t* bytes, const uint64_t* offsets, uint32_t n_strings,
+                             uint32_t n_threads, uint32_t cap, uint32_t* il, uint32_t* ol, double* w,
+                             int32_t* status, uint32_t* lens, double* finals, double* totals,
+                             uint64_t* sum_tuples, uint64_t* sum_relax) {
+  return batch_bytes_impl(fst, bytes, offsets, n_strings, n_threads, cap, il, ol, w, status, lens, finals, totals, sum_tuples, sum_relax, true);
 }
 
 // string.zig:64-97 over a path result expressed as label arrays is trivial; the
