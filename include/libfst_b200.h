@@ -190,7 +190,10 @@ typedef struct {
                                  change the result (identical output, proven in DESIGN.md) */
   uint32_t engine;            /* kernel choice for byte-string batches: 0 = auto, 1 = general
                                  warp kernel, 2 = lean kernel + hash table, 3 = lean kernel +
-                                 dense (position x state) table; all produce identical output */
+                                 dense (position x state) table, 4 = wave kernel (one warp per
+                                 string, a ready word of up to 32 tuples per step; table auto),
+                                 5 = wave + hash table, 6 = wave + dense table, 7 = lean kernel
+                                 (table auto); all produce identical output */
   uint32_t semantics;         /* 0 = lazy: fst_compose_frozen_shortest_path (compose-shortest-path.zig);
                                  1 = eager: the result of fst_compose_frozen followed by fst_shortest_path
                                  (compose.zig:29-198 + shortest-path.zig:18-139; other tie-breaks),

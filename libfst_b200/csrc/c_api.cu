@@ -611,7 +611,7 @@ FstError fst_b200_configure(const FstB200Config* cfg) {
   uint32_t g = cfg->lanes_per_string;
   if (!(g == 0 || g == 4 || g == 8 || g == 16 || g == 32)) return FST_INVALID_ARG;
   Config& c = global_config();
-  if (cfg->engine > 3 || cfg->semantics > 1) return FST_INVALID_ARG;
+  if (cfg->engine > 7 || cfg->semantics > 1) return FST_INVALID_ARG;
   c.workspace_bytes = cfg->workspace_bytes; c.lanes_per_string = g; c.tuples_hint = cfg->tuples_hint; c.exhaustive = cfg->exhaustive; c.engine = cfg->engine; c.semantics = cfg->semantics;
   return FST_OK;
 }

@@ -89,13 +89,14 @@ struct LeanLayout {
   uint32_t smem_words;   // u32 words of shared memory per group
 };
 // `tab_entries`: dense = (max_len + 1) * S * 2 records of 16 B; hash = slots of 32 B.
-__host__ __device__ inline LeanLayout lean_layout(int G, bool dense, uint64_t tab_entries, uint32_t tuple_cap, uint32_t chunk_cap) {
+__host__ __device__ inline LeanLayout lean_layout(int G, bool dense, uint64_t tab_entries, uint32_t tuple_cap, uint32_t chunk_cap,
+                                                  bool crec = false) {
   LeanLayout L;
   auto al = [](uint64_t x) { return (x + 127) & ~127ull; };
   const uint32_t ids_per_line = 32u * (uint32_t)G;
   const uint32_t lines = (tuple_cap + ids_per_line - 1) / ids_per_line;
   L.n1 = (lines + 31) / 32;
-  L.tab_bytes = al(tab_entries * (dense ? 16ull : 32ull));
+  L.tab_bytes = al(tab_entries * (dense ? (crec ? 8ull : 16ull) : 32ull));
   L.l0_bytes = al((uint64_t)lines * G * 4);
   L.off_tab = 0;
   L.off_keyof = L.tab_bytes;
@@ -160,13 +161,14 @@ struct LeanState {
   uint32_t wline;                // line held in the window, kNone = none
   unsigned long long last;       // bit pattern of the current level distance
   unsigned long long future_min; // per lane: smallest distance pushed beyond the current level
-  unsigned long long relax_calls;
+  unsigned long long relax_calls;   // PER-LANE partial count (summed over the warp when the kernel ends)
   bool low_pending;              // a ready id below the window was inserted
   bool overflow;                 // tuple capacity exhausted -> retry with a larger arena
   bool heap_overflow;            // radix-heap pool exhausted -> retry with a deeper pool
   bool sorted;                   // the radix heap exists (a second level was needed)
   bool bfs_started;              // the id -> key array holds BFS numbers (a full table reset is needed after an abort)
   bool stuck;                    // safety valve tripped (see the kernel loop)
+  bool wide;                     // PER-LANE: a distance did not fit the compact record (table kind 2) -> retry with 16-byte records
   uint32_t occ;                  // eager BFS phase: records in the table = search tuples + tuples first met by the BFS
 };
 
@@ -175,15 +177,21 @@ struct LeanState {
 //   hash table:  64-bit key (P << 32) | SF.
 //   dense table: index P * dense_stride + SF; id -> key array holds the COMPACT 32-bit form
 //                (P << key_sbits) | SF  (fits: the dense table has < 2^30 records).
-template <bool DENSE> struct LeanKeyT { using type = unsigned long long; };
-template <> struct LeanKeyT<true> { using type = uint32_t; };
+// Table kind (template parameter DENSE of everything below): 0 = hash table of 32-byte slots, 1 = dense table of
+// 16-byte records {dist f64, id, prev}, 2 = dense table of COMPACT 8-byte records  dist:20 | id:22 | prev:22  for
+// transducers whose weights are all small non-negative integers (every distance is then an integer, exact in
+// both forms): half the table bytes per string, so more strings fit HBM and a DRAM sector holds four records.
+// All-ones = never touched in every kind.  A distance that does not fit 20 bits marks the string for a retry with
+// 16-byte records (LeanState::wide).
+constexpr uint32_t kCrecNone = 0x3FFFFFu;          // 22-bit id / prev: none
+constexpr double kCrecMaxDist = 1048575.0;         // 20-bit distance
 
-template <bool DENSE>
+template <int DENSE>
 __device__ __forceinline__ void lean_keyof_store(const SearchParams& p, const LeanCtx& c, uint32_t id, uint32_t P, uint32_t SF) {
   if (DENSE) reinterpret_cast<uint32_t*>(LEAN_KEYOF(p, c))[id] = (P << p.key_sbits) | SF;
   else reinterpret_cast<unsigned long long*>(LEAN_KEYOF(p, c))[id] = ((unsigned long long)P << 32) | SF;
 }
-template <bool DENSE>
+template <int DENSE>
 __device__ __forceinline__ void lean_keyof_load(const SearchParams& p, const LeanCtx& c, uint32_t id, uint32_t& P, uint32_t& SF) {
   if (DENSE) {
     const uint32_t k = reinterpret_cast<const uint32_t*>(LEAN_KEYOF(p, c))[id];
@@ -203,10 +211,16 @@ __device__ __forceinline__ uint32_t lean_dense_pos(const SearchParams& p, uint32
 }
 // Find the record of key (P, SF): position and contents; id == kNone <=> not present (hash: `pos` is then
 // the empty slot that ended the probe — pass it to lean_claim before storing).
-template <bool DENSE>
+template <int DENSE>
 __device__ __forceinline__ void lean_lookup(const SearchParams& p, const LeanCtx& c, uint32_t P, uint32_t SF, uint32_t& pos, double& dist,
                                             uint32_t& id, uint32_t& prev) {
-  if (DENSE) {
+  if (DENSE == 2) {
+    pos = lean_dense_pos(p, P, SF);
+    const uint2 v = *reinterpret_cast<const uint2*>(c.base + (uint64_t)pos * 8);   // x = low word: id:10 low bits | prev:22 ; y = dist:20 | id:12 high bits
+    const uint32_t i = ((v.y & 0xFFFu) << 10) | (v.x >> 22), pr = v.x & kCrecNone;
+    id = i == kCrecNone ? kNone : i; prev = pr == kCrecNone ? kNone : pr;
+    dist = i == kCrecNone ? d_inf() : (double)(v.y >> 12);
+  } else if (DENSE) {
     pos = lean_dense_pos(p, P, SF);
     const uint4 v = *reinterpret_cast<const uint4*>(c.base + (uint64_t)pos * 16);
     dist = __hiloint2double((int)v.y, (int)v.x); id = v.z; prev = v.w;
@@ -230,7 +244,7 @@ __device__ __forceinline__ void lean_lookup(const SearchParams& p, const LeanCtx
 }
 // Hash table: claim a slot for the new key, starting at the empty position the probe found (other
 // lanes of the group insert other keys concurrently).  Dense table: nothing to do.
-template <bool DENSE>
+template <int DENSE>
 __device__ __forceinline__ uint32_t lean_claim(const SearchParams& p, const LeanCtx& c, uint32_t P, uint32_t SF, uint32_t pos) {
   if (DENSE) return pos;
   const unsigned long long K = ((unsigned long long)P << 32) | SF;
@@ -243,8 +257,13 @@ __device__ __forceinline__ uint32_t lean_claim(const SearchParams& p, const Lean
 }
 // Write a record.  The hash variant rewrites the key half too: plain stores keep this SM's L1 copy of the
 // sector consistent with what later plain-load probes must see (the claiming CAS acts on L2 only).
-template <bool DENSE>
+template <int DENSE>
 __device__ __forceinline__ void lean_store(const LeanCtx& c, uint32_t pos, uint32_t P, uint32_t SF, double dist, uint32_t id, uint32_t prev) {
+  if (DENSE == 2) {
+    const uint32_t d = __double2uint_rn(fmin(dist, kCrecMaxDist)), pr = prev & kCrecNone;   // kNone -> kCrecNone
+    *reinterpret_cast<uint2*>(c.base + (uint64_t)pos * 8) = make_uint2((id << 22) | pr, (d << 12) | ((id >> 10) & 0xFFFu));
+    return;
+  }
   const uint4 v = make_uint4((uint32_t)__double2loint(dist), (uint32_t)__double2hiint(dist), id, prev);
   if (DENSE) {
     *reinterpret_cast<uint4*>(c.base + (uint64_t)pos * 16) = v;
@@ -254,7 +273,7 @@ __device__ __forceinline__ void lean_store(const LeanCtx& c, uint32_t pos, uint3
     sl[1] = v;
   }
 }
-template <bool DENSE>
+template <int DENSE>
 __device__ __forceinline__ double lean_dist_of_id(const SearchParams& p, const LeanCtx& c, uint32_t id) {
   uint32_t P, SF, pos, i2, pr; double d;
   lean_keyof_load<DENSE>(p, c, id, P, SF);
@@ -295,7 +314,7 @@ __device__ __forceinline__ void lean_window_evict(const SearchParams& p, const G
   g.sync();
 }
 // Load the lowest non-empty line into the window.  False: the ready set is empty.
-template <int G, bool DENSE>
+template <int G, int DENSE>
 __device__ __forceinline__ bool lean_window_next(const SearchParams& p, const Group<G>& g, const LeanCtx& c, LeanState& st) {
   const uint32_t words = min(p.n1, (st.n_tuples >> (10 + LgG<G>::v)) + 1u);
   uint32_t* l1 = LEAN_L1(c, G);
@@ -412,7 +431,7 @@ __device__ __forceinline__ unsigned long long lean_group_min_u64(const Group<G>&
 
 // Build the radix heap: every tuple whose distance is above the level just finished is unsettled and
 // belongs to the future set (one scan, once per string, only if a second level is needed).
-template <int G, bool DENSE>
+template <int G, int DENSE>
 __device__ __forceinline__ void lean_build_radix(const SearchParams& p, const Group<G>& g, const LeanCtx& c, LeanState& st) {
   st.sorted = true;
   const uint32_t n = st.n_tuples;
@@ -429,7 +448,7 @@ __device__ __forceinline__ void lean_build_radix(const SearchParams& p, const Gr
 
 // Advance to the next distance level; false = the search is finished (no valid entry left, or no
 // remaining tuple can change the result).
-template <int G, bool DENSE>
+template <int G, int DENSE>
 __device__ __forceinline__ bool lean_advance_level(const SearchParams& p, const Group<G>& g, const LeanCtx& c, LeanState& st) {
   const uint32_t* cold = LEAN_COLD(p, c, G);
   const bool have_best = cold[kcHaveBest] != 0;
@@ -506,21 +525,23 @@ __device__ __forceinline__ bool lean_advance_level(const SearchParams& p, const 
 
 // ── one relaxation per lane ──
 // `active` lanes hold DISTINCT targets (the static search records fold parallel arcs, see
-// device_types.cuh `sarc`); `n_cand` = all arcs of the expansion (the reference's relax calls).
+// device_types.cuh `sarc`); `my_cnt` = this lane's share of the reference's relax calls (all arcs of the
+// expansion, folded ones included).
 // `first`: lanes that precede the other lanes in the reference's expansion order (match arcs
 // :182-202 before input-epsilon arcs :254-278); only used to number newly discovered tuples.
 // HOT: see lean_ballot — every lane of the warp calls, groups without work pass active = false.
-template <int G, bool DENSE, bool HOT, bool EAGER = true>
+template <int G, int DENSE, bool HOT, bool EAGER = true>
 __device__ __forceinline__ void lean_relax(const SearchParams& p, const Group<G>& g, const LeanCtx& c, LeanState& st, uint32_t cur_id,
-                                           uint32_t n_cand, bool active, uint32_t P, uint32_t SF, double wmin, unsigned first,
+                                           uint32_t my_cnt, bool active, uint32_t P, uint32_t SF, double wmin, unsigned first,
                                            bool bfs = false, double bfs_dist = 0.0) {
   // NOTE: the search step and the BFS step of the eager semantics share every collective CALL SITE below —
   // groups of one warp can be in different modes, and a warp-wide collective only matches itself.
-  st.relax_calls += n_cand;
+  st.relax_calls += my_cnt;
   uint32_t pos = 0, old_id = 0, old_prev = kNone; double old_dist = d_inf();
   if (active) lean_lookup<DENSE>(p, c, P, SF, pos, old_dist, old_id, old_prev);
   // smallest new distance over the parallel arcs (fl(c + w) is monotone in w)
   const double nd = (bfs ? bfs_dist : __longlong_as_double((long long)st.last)) + wmin;
+  if (DENSE == 2 && active && nd > kCrecMaxDist) st.wide = true;
   const bool untouched = active && old_id == kNone;
   // search: a target is new when it has no record; BFS: when it has no BFS number yet (compose.zig:77-91)
   const bool is_new = bfs ? (active && (untouched || !(old_id & kBfsFlag))) : untouched;
@@ -592,10 +613,10 @@ __device__ inline bool lean_recover_arc(const DevFstView& F, const LhsBytes& lhs
 
 // Start a string: initial tuple id 0, dist One, ready at level 0 (compose-shortest-path.zig:146-153).
 // Precondition (invariant between strings): table untouched-state, ready bitmap, window and summary zero.
-template <int G, bool DENSE>
+template <int G, int DENSE>
 __device__ __forceinline__ void lean_begin(const SearchParams& p, const Group<G>& g, const LeanCtx& c, LeanState& st) {
   st.n_tuples = 1; st.wline = 0; st.relax_calls = 0; st.last = 0; st.future_min = ~0ull;
-  st.low_pending = false; st.overflow = false; st.heap_overflow = false; st.sorted = false; st.bfs_started = false; st.stuck = false; st.occ = 0;
+  st.low_pending = false; st.overflow = false; st.heap_overflow = false; st.sorted = false; st.bfs_started = false; st.stuck = false; st.occ = 0; st.wide = false;
   uint32_t* cold = LEAN_COLD(p, c, G);
   if (g.lane == 0) {
     const uint32_t SF = p.fst.start << 1;
@@ -616,7 +637,7 @@ __device__ __forceinline__ void lean_begin(const SearchParams& p, const Group<G>
 // False: this group's search is over (queue empty, early stop, or an overflow).
 // `mode`: 0 = this lane's group is not running, 1 = search step, 2 = BFS step of the eager semantics (pops are
 // the lattice states in FIFO order: st.wline is the cursor).
-template <int G, bool DENSE, bool SLAB, bool EAGER>
+template <int G, int DENSE, bool SLAB, bool EAGER>
 __device__ __forceinline__ bool lean_step(const SearchParams& p, const Group<G>& g, const LeanCtx& c, LeanState& st, const LhsBytes& lhs,
                                           uint32_t mode) {
   constexpr bool HOT = true;
@@ -703,9 +724,15 @@ __device__ __forceinline__ bool lean_step(const SearchParams& p, const Group<G>&
   uint4 rec = make_uint4(0, 0, 0, 0);
   uint32_t x = 0xFFFFFFFDu;
   bool big = false;
+  // 8 lanes per string read the LEADER slab: one record per (ilabel, nextstate) group, labels first then the
+  // input-epsilon records (lane order == expansion order), x = ilabel | folded arc count << 16
+  constexpr bool LEADERS = SLAB && G == 8;
   if (live) {
     x = s1 < lhs.len ? (uint32_t)__ldg(lhs.s + s1) + 1u : 0xFFFFFFFDu;
-    if (SLAB) {
+    if (LEADERS) {
+      sa = __ldg(&F.wslab[(uint64_t)s2 * kWaveSlots + g.lane]);
+      big = sa.x == kWaveBig;
+    } else if (SLAB) {
       sa = __ldg(&F.slab[(uint64_t)s2 * G + g.lane]);
       big = sa.x == 0xFFFFFFFEu;
     } else {
@@ -715,11 +742,12 @@ __device__ __forceinline__ bool lean_step(const SearchParams& p, const Group<G>&
       if (!big && g.lane < deg) sa = __ldg(&F.sarc[rec.x + g.lane]);
     }
   }
-  const bool is_match = sa.x == x;                 // x is never 0xFFFFFFFF / 0xFFFFFFFE (labels are byte + 1)
-  const bool is_eps = sa.x == 0u;                  // ilabel 0 only occurs in the epsilon prefix
-  const unsigned first = lean_ballot<G, HOT>(g, is_match);
-  const unsigned candm = lean_ballot<G, HOT>(g, is_match || is_eps);
-  lean_relax<G, DENSE, HOT, EAGER>(p, g, c, st, cur_id, __popc(candm), (is_match || is_eps) && !(sa.y >> 31), is_match ? s1 + 1u : s1,
+  const uint32_t lab = LEADERS ? (sa.x & 0xFFFFu) : sa.x;
+  const bool is_match = lab == x;                  // x is never 0xFFFFFFFF / 0xFFFFFFFE / 0xFFFF (labels are byte + 1)
+  const bool is_eps = lab == 0u;                   // ilabel 0 only occurs in the epsilon records
+  const unsigned first = LEADERS ? Group<G>::kBits : lean_ballot<G, HOT>(g, is_match);
+  const uint32_t my_cnt = (is_match || is_eps) ? (LEADERS ? (sa.x >> 16) : 1u) : 0u;
+  lean_relax<G, DENSE, HOT, EAGER>(p, g, c, st, cur_id, my_cnt, (is_match || is_eps) && !(sa.y >> 31), is_match ? s1 + 1u : s1,
                             (sa.y << 1) | (is_match ? 0u : 1u), __hiloint2double((int)sa.w, (int)sa.z), first, bfs, bfs_dist);
   if (live && big) {
     // a state wider than the group: binary-searched match range, then the epsilon prefix, G arcs per step
@@ -730,7 +758,7 @@ __device__ __forceinline__ bool lean_step(const SearchParams& p, const Group<G>&
       const bool cand = cb + g.lane < hi;
       uint4 sb = make_uint4(0, 0x80000000u, 0, 0);
       if (cand) sb = __ldg(&F.sarc[cb + g.lane]);
-      lean_relax<G, DENSE, false, EAGER>(p, g, c, st, cur_id, min(hi - cb, (uint32_t)G), cand && !(sb.y >> 31), s1 + 1u, sb.y << 1,
+      lean_relax<G, DENSE, false, EAGER>(p, g, c, st, cur_id, cand ? 1u : 0u, cand && !(sb.y >> 31), s1 + 1u, sb.y << 1,
                                   __hiloint2double((int)sb.w, (int)sb.z), Group<G>::kBits, bfs, bfs_dist);
       g.sync();
     }
@@ -738,7 +766,7 @@ __device__ __forceinline__ bool lean_step(const SearchParams& p, const Group<G>&
       const bool cand = cb + g.lane < rec.y;
       uint4 sb = make_uint4(0, 0x80000000u, 0, 0);
       if (cand) sb = __ldg(&F.sarc[cb + g.lane]);
-      lean_relax<G, DENSE, false, EAGER>(p, g, c, st, cur_id, min(rec.y - cb, (uint32_t)G), cand && !(sb.y >> 31), s1, (sb.y << 1) | 1u,
+      lean_relax<G, DENSE, false, EAGER>(p, g, c, st, cur_id, cand ? 1u : 0u, cand && !(sb.y >> 31), s1, (sb.y << 1) | 1u,
                                   __hiloint2double((int)sb.w, (int)sb.z), Group<G>::kBits, bfs, bfs_dist);
       g.sync();
     }
@@ -748,7 +776,7 @@ __device__ __forceinline__ bool lean_step(const SearchParams& p, const Group<G>&
 
 // Start the BFS phase of the eager semantics after the search: the initial tuple is lattice state 0
 // (compose.zig:57-61); st.wline becomes the FIFO cursor, st.n_tuples the number of states numbered so far.
-template <int G, bool DENSE>
+template <int G, int DENSE>
 __device__ __forceinline__ void lean_bfs_begin(const SearchParams& p, const Group<G>& g, const LeanCtx& c, LeanState& st) {
   uint32_t* cold = LEAN_COLD(p, c, G);
   g.sync();
@@ -766,7 +794,7 @@ __device__ __forceinline__ void lean_bfs_begin(const SearchParams& p, const Grou
 }
 
 // End of a string: back-track, emit the reversed path into the pool, restore the arena invariants.
-template <int G, bool DENSE>
+template <int G, int DENSE>
 __device__ __forceinline__ int32_t lean_finish(const SearchParams& p, const Group<G>& g, const LeanCtx& c, const LeanState& st,
                                                const LhsBytes& lhs, uint32_t* out_path_len, uint64_t* out_pool_off, double* out_final_w) {
   const DevFstView& F = p.fst;
@@ -780,7 +808,10 @@ __device__ __forceinline__ int32_t lean_finish(const SearchParams& p, const Grou
   const bool have_best = cold[kcHaveBest] != 0;
   const uint32_t best_id = cold[kcBestId];
   const double best_fw = __hiloint2double((int)cold[kcBestFwHi], (int)cold[kcBestFwLo]);
-  if (st.stuck) {
+  const bool wide = DENSE == 2 && g.any(st.wide);
+  if (wide) {
+    status = kStRetryWide;
+  } else if (st.stuck) {
     status = kStInternal;
   } else if (st.overflow) {
     status = kStRetry;
@@ -834,22 +865,24 @@ __device__ __forceinline__ int32_t lean_finish(const SearchParams& p, const Grou
   // Restore the arena invariants for the next string: table untouched-state, bitmaps zero.
   g.sync();
   const uint32_t n = st.n_tuples;
-  const bool aborted = st.overflow || st.heap_overflow || st.stuck;
+  const bool aborted = st.overflow || st.heap_overflow || st.stuck || wide;
   const bool mixed = st.bfs_started && aborted;   // id -> key array is part search ids, part BFS numbers
   if (mixed) {
     uint4* t = reinterpret_cast<uint4*>(c.base);
-    const uint64_t vecs = p.tab_entries * (DENSE ? 1ull : 2ull);
+    const uint64_t vecs = DENSE == 2 ? (p.tab_entries + 1) / 2 : p.tab_entries * (DENSE ? 1ull : 2ull);
     for (uint64_t i = g.lane; i < vecs; i += G) t[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
   } else if (DENSE) {
     if ((uint64_t)n * 4 < p.tab_entries) {
       for (uint32_t i = g.lane; i < n; i += G) {
         uint32_t P, SF;
-        lean_keyof_load<true>(p, c, i, P, SF);
-        *reinterpret_cast<uint4*>(c.base + (uint64_t)lean_dense_pos(p, P, SF) * 16) = make_uint4(~0u, ~0u, ~0u, ~0u);
+        lean_keyof_load<1>(p, c, i, P, SF);
+        if (DENSE == 2) *reinterpret_cast<uint2*>(c.base + (uint64_t)lean_dense_pos(p, P, SF) * 8) = make_uint2(~0u, ~0u);
+        else *reinterpret_cast<uint4*>(c.base + (uint64_t)lean_dense_pos(p, P, SF) * 16) = make_uint4(~0u, ~0u, ~0u, ~0u);
       }
     } else {
       uint4* t = reinterpret_cast<uint4*>(c.base);
-      for (uint64_t i = g.lane; i < p.tab_entries; i += G) t[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+      const uint64_t vecs = DENSE == 2 ? (p.tab_entries + 1) / 2 : p.tab_entries;   // the table is padded to 128 bytes
+      for (uint64_t i = g.lane; i < vecs; i += G) t[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
     }
   } else {
     // two phases: resolve every tuple's slot first (probing needs intact chains), then clear
@@ -880,7 +913,7 @@ __device__ __forceinline__ int32_t lean_finish(const SearchParams& p, const Grou
 // Persistent batch kernel.  One loop; an iteration is one step of this group's string (fetch the next
 // string / one pop / finish), with a warp-wide reconvergence at the top so that the 16-lane groups of a
 // warp stay in lockstep.
-template <int G, bool DENSE, bool SLAB, bool EAGER>
+template <int G, int DENSE, bool SLAB, bool EAGER>
 __global__ void __launch_bounds__(128, FSTB_LEAN_MINBLOCKS) csp_batch_lean_kernel(const __grid_constant__ SearchParams p) {
   extern __shared__ __align__(16) uint32_t smem_all[];
   const Group<G> g;
@@ -896,7 +929,7 @@ __global__ void __launch_bounds__(128, FSTB_LEAN_MINBLOCKS) csp_batch_lean_kerne
   uint32_t steps = 0;   // safety valve: steps of the current string (tuple_cap <= 4 M, so the bound fits 32 bits)
   LeanState st;
   st.n_tuples = 0; st.wline = kNone; st.relax_calls = 0; st.last = 0; st.future_min = ~0ull;
-  st.low_pending = false; st.overflow = false; st.heap_overflow = false; st.sorted = false; st.bfs_started = false; st.stuck = false; st.occ = 0;
+  st.low_pending = false; st.overflow = false; st.heap_overflow = false; st.sorted = false; st.bfs_started = false; st.stuck = false; st.occ = 0; st.wide = false;
   LhsBytes lhs; lhs.s = nullptr; lhs.len = 0;
   unsigned long long relax_total = 0, tuple_total = 0;
   for (;;) {
@@ -942,10 +975,11 @@ __global__ void __launch_bounds__(128, FSTB_LEAN_MINBLOCKS) csp_batch_lean_kerne
       phase = kFetch;
     }
   }
-  if (g.lane == 0) {
-    if (relax_total) atomicAdd(p.relax_counter, relax_total);
-    if (tuple_total) atomicAdd(p.tuple_counter, tuple_total);
-  }
+  // relax counts are per-lane partial sums: add up the warp
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) relax_total += __shfl_xor_sync(0xFFFFFFFFu, relax_total, o);
+  if ((threadIdx.x & 31u) == 0 && relax_total) atomicAdd(p.relax_counter, relax_total);
+  if (g.lane == 0 && tuple_total) atomicAdd(p.tuple_counter, tuple_total);
 }
 
 }  // namespace fstb200

@@ -6,6 +6,8 @@
 namespace fstb200 {
 
 constexpr uint32_t kNone = 0xFFFFFFFFu;
+constexpr uint32_t kWaveSlots = 8;            // search records per transducer state in the leader slab (`wslab`)
+constexpr uint32_t kWaveBig = 0xFFFFFFFEu;    // leader slab marker (every slot): the state has more records than the slab holds
 
 // Frozen transducer in HBM (struct-of-arrays CSR, frozen arc order unchanged —
 // reference src/fst.zig:16-40 and SURVEY App. D):
@@ -33,6 +35,12 @@ struct DevFstView {
   // Saves the state_rec hop of the per-pop dependent load chain.  slab_lanes == 0: not built.
   const uint4* slab;
   uint32_t slab_lanes, pad0;
+  // optional leader slab (lean kernel with 8 lanes per string, wave kernel): state s owns wslab[s * 8 .. +8): its LEADER search records only (one per
+  // (ilabel, nextstate) group), labels 1..256 in frozen order first, then the input-epsilon records, as
+  // {ilabel | folded arc count << 16, nextstate, wmin(f64 as 2xu32)}; unused slots hold 0xFFFFFFFF in x; a state
+  // with more than 8 records (or a group of more than 65535 arcs) holds the marker 0xFFFFFFFE in every slot.
+  // Arcs with ilabel > 256 never match a byte string and are left out.  null: not built.
+  const uint4* wslab;
 };
 
 // General (non-linear) left operand as CSR in STORED arc order
@@ -64,7 +72,7 @@ constexpr uint32_t kSettledBit = 0x80000000u;
 
 // Per-string status written by the search kernel (internal; the C ABI maps
 // kRetry to a retry pass and finally to FST_B200_TOO_LARGE).
-enum : int32_t { kStPath = 0, kStNoPath = 1, kStCycle = 2, kStTooLarge = 3, kStInternal = 4, kStRetry = 100, kStRetryHeap = 101 };
+enum : int32_t { kStPath = 0, kStNoPath = 1, kStCycle = 2, kStTooLarge = 3, kStInternal = 4, kStRetry = 100, kStRetryHeap = 101, kStRetryWide = 102 };
 
 // Reversed path arc as written to the path pool by the search kernel.
 struct __align__(16) PoolArc { uint32_t ilabel, olabel; double weight; };
@@ -100,6 +108,7 @@ struct SearchParams {
   unsigned long long* pool_cursor;
   unsigned long long* relax_counter;
   unsigned long long* tuple_counter;
+  unsigned long long* wave_stats;   // optional [4]: chunk steps, tuples popped by chunks, single-pop steps, abandoned chunks
   // outputs (indexed by string index)
   int32_t* status;
   uint32_t* path_len;

@@ -17,6 +17,7 @@
 #include "csp_kernels.cuh"
 #include "csp_warp.cuh"
 #include "csp_lean.cuh"
+#include "csp_wave.cuh"
 #include "host_fst.hpp"
 
 namespace fstb200 {
@@ -36,7 +37,8 @@ struct Config {
   uint32_t lanes_per_string = 0;
   uint32_t tuples_hint = 0;
   uint32_t exhaustive = 0;
-  uint32_t engine = 0;       // 0 auto, 1 general warp kernel, 2 lean + hash table, 3 lean + dense table
+  uint32_t engine = 0;       // 0 auto, 1 general warp kernel, 2 lean + hash table, 3 lean + dense table,
+                             // 4 wave (table auto), 5 wave + hash table, 6 wave + dense table, 7 lean (table auto)
   uint32_t semantics = 0;    // 0 lazy (composeShortestPath), 1 eager (compose then shortestPath; lean kernel only)
 };
 inline Config& global_config() { static Config c; return c; }
@@ -47,11 +49,15 @@ struct DeviceFst {
   DevFstView view{};
   void* block = nullptr;   // one allocation holding all arrays
   void* slab_block = nullptr;   // fixed-stride search records (lean kernel), may be null
+  void* wslab_block = nullptr;  // leader-only fixed-stride search records (wave kernel), may be null
+  bool int_weights = false;     // every finite arc / final weight is a non-negative integer <= 4095: compact 8-byte table records apply
+  bool wave_ok = false;         // wave slab built and at least 90 % of the states fit it
   size_t bytes = 0;
   bool serial = false;     // negative weights: literal sequential relax
   bool lean_ok = false;    // all arc weights finite and >= 0: the lean batched kernel applies
   uint32_t hint_tuples = 0;  // largest per-string tuple count seen so far (arena sizing)
   uint32_t hint_heap_mult = 1;  // radix-heap pool depth that sufficed so far (lean kernel)
+  bool crec_failed = false;     // a search outgrew the compact records once: do not try them again
   uint32_t lean_lanes = 32;     // lanes per string of the lean kernel: smallest of 8/16/32 that covers 90% of the states' arcs in one step
 };
 
@@ -113,7 +119,12 @@ inline cudaError_t upload_fst(const HostFrozen& f, int device, DeviceFst** out) 
       }
     }
   }
+  bool int_weights = lean_ok;
+  for (uint32_t a = 0; a < A && int_weights; a++) int_weights = ar[a].weight >= 0.0 && ar[a].weight <= 4095.0 && ar[a].weight == std::floor(ar[a].weight);
+  for (uint32_t s = 0; s < S && int_weights; s++)
+    if (!std::isinf(st[s].final_weight)) int_weights = st[s].final_weight >= 0.0 && st[s].final_weight <= 4095.0 && st[s].final_weight == std::floor(st[s].final_weight);
   auto d = new DeviceFst();
+  d->int_weights = int_weights;
   d->device = device; d->bytes = total; d->serial = f.has_negative; d->lean_ok = lean_ok;
   cudaError_t e = cudaMalloc(&d->block, total);
   if (e != cudaSuccess) { delete d; return e; }
@@ -132,7 +143,7 @@ inline cudaError_t upload_fst(const HostFrozen& f, int device, DeviceFst** out) 
     d->lean_lanes = (uint64_t)le8 * 10 >= (uint64_t)S * 9 ? 8 : ((uint64_t)le16 * 10 >= (uint64_t)S * 9 ? 16 : 32);
   }
   d->view.slab = nullptr; d->view.slab_lanes = 0; d->view.pad0 = 0;
-  const uint32_t GL = d->lean_lanes;
+  const uint32_t GL = d->lean_lanes == 8 ? 16 : d->lean_lanes;   // 8 lanes read the leader slab (below); this one serves 16 / 32
   if (lean_ok && (uint64_t)S * GL * 16 <= (64ull << 20)) {
     // fixed-stride copy of the search records: one load per lane per pop without the state_rec hop
     std::vector<uint4> slab((size_t)S * GL, make_uint4(0xFFFFFFFFu, 0x80000000u, 0, 0));
@@ -148,6 +159,43 @@ inline cudaError_t upload_fst(const HostFrozen& f, int device, DeviceFst** out) 
       cudaGetLastError(); cudaFree(d->slab_block); d->slab_block = nullptr;
     }
   }
+  d->view.wslab = nullptr;
+  if (lean_ok && (uint64_t)S * kWaveSlots * 16 <= (256ull << 20)) {
+    std::vector<uint4> ws((size_t)S * kWaveSlots, make_uint4(0xFFFFFFFFu, 0u, 0u, 0u));
+    uint32_t n_big = 0;
+    std::vector<uint4> lab, eps;
+    for (uint32_t s = 0; s < S; s++) {
+      const uint32_t b = st[s].arc_offset, e = b + st[s].num_arcs;
+      lab.clear(); eps.clear();
+      bool big = false;
+      for (uint32_t a = b; a < e && !big; a++) {
+        if (sa[a].y >> 31) continue;                       // folded into its leader
+        if (sa[a].x > 256u) continue;                      // never matches a byte
+        uint32_t cnt = 0;                                  // arcs of the group (the leader's run of equal ilabel)
+        for (uint32_t a2 = a; a2 < e && ar[a2].ilabel == ar[a].ilabel; a2++) cnt += ar[a2].nextstate == ar[a].nextstate;
+        if (cnt > 0xFFFFu) { big = true; break; }
+        const uint4 r = make_uint4(sa[a].x | (cnt << 16), sa[a].y, sa[a].z, sa[a].w);
+        (sa[a].x == 0u ? eps : lab).push_back(r);
+      }
+      if (big || lab.size() + eps.size() > kWaveSlots) {
+        for (uint32_t k = 0; k < kWaveSlots; k++) ws[(size_t)s * kWaveSlots + k] = make_uint4(kWaveBig, 0x80000000u, 0u, 0u);
+        n_big++;
+        continue;
+      }
+      size_t k = 0;
+      for (const uint4& r : lab) ws[(size_t)s * kWaveSlots + k++] = r;
+      for (const uint4& r : eps) ws[(size_t)s * kWaveSlots + k++] = r;
+    }
+    if (cudaMalloc(&d->wslab_block, ws.size() * 16) == cudaSuccess &&
+        cudaMemcpy(d->wslab_block, ws.data(), ws.size() * 16, cudaMemcpyHostToDevice) == cudaSuccess) {
+      d->view.wslab = static_cast<const uint4*>(d->wslab_block);
+      d->wave_ok = (uint64_t)n_big * 10 <= (uint64_t)S;
+      // at least 90 % of the states fit 8 leader records: 8 lanes per string reading the leader slab
+      if (d->wave_ok) d->lean_lanes = 8;
+    } else {
+      cudaGetLastError(); cudaFree(d->wslab_block); d->wslab_block = nullptr;
+    }
+  }
   *out = d;
   return cudaSuccess;
 }
@@ -157,21 +205,24 @@ inline void free_device_fst(DeviceFst* d) {
   if (cur != d->device) cudaSetDevice(d->device);
   cudaFree(d->block);
   cudaFree(d->slab_block);
+  cudaFree(d->wslab_block);
   if (cur != d->device) cudaSetDevice(cur);
   delete d;
 }
 
 // small helper kernels (plumbing)
-__global__ void collect_retry_kernel(const int32_t* status, uint32_t n, uint32_t* order, uint32_t* count, uint32_t* heap_count) {
+__global__ void collect_retry_kernel(const int32_t* status, uint32_t n, uint32_t* order, uint32_t* count, uint32_t* heap_count,
+                                     uint32_t* wide_count) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n && (status[i] == kStRetry || status[i] == kStRetryHeap)) {
+  if (i < n && (status[i] == kStRetry || status[i] == kStRetryHeap || status[i] == kStRetryWide)) {
     order[atomicAdd(count, 1u)] = i;
     if (status[i] == kStRetryHeap) atomicAdd(heap_count, 1u);
+    if (status[i] == kStRetryWide) atomicAdd(wide_count, 1u);
   }
 }
 __global__ void mark_too_large_kernel(int32_t* status, uint32_t* path_len, uint32_t n) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n && (status[i] == kStRetry || status[i] == kStRetryHeap)) { status[i] = kStTooLarge; path_len[i] = 0; }
+  if (i < n && (status[i] == kStRetry || status[i] == kStRetryHeap || status[i] == kStRetryWide)) { status[i] = kStTooLarge; path_len[i] = 0; }
 }
 __global__ void fill_retry_kernel(int32_t* status, uint32_t* path_len, uint32_t n) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -216,6 +267,7 @@ class Engine {
     e = cudaDeviceGetAttribute(&en->sm_count, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) { delete en; *err = e; return nullptr; }
     e = cudaMalloc(&en->d_small_, 256);
+    if (e == cudaSuccess) e = cudaMemset(en->d_small_, 0, 256);
     if (e != cudaSuccess) { delete en; *err = e; return nullptr; }
     e = cudaMallocHost(&en->h_small_, 256);
     if (e != cudaSuccess) { delete en; *err = e; return nullptr; }
@@ -249,6 +301,7 @@ class Engine {
 
     uint32_t tuple_cap = cfg.tuples_hint ? cfg.tuples_hint : (fst->hint_tuples ? fst->hint_tuples + fst->hint_tuples / 4 + 64 : 4096);
     uint32_t n_items = n, heap_mult = fst->hint_heap_mult;
+    bool crec_ok = fst->int_weights && !fst->crec_failed;   // compact table records until a distance outgrows them
     const uint32_t* d_order = nullptr;
     auto too_large = [&]() {
       mark_too_large_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_status, d_path_len_, n);
@@ -257,7 +310,7 @@ class Engine {
     for (uint32_t pass = 0;; pass++) {
       bc->passes++;
       Geom gm;
-      if (!geometry(cfg, fst, max_len, tuple_cap, heap_mult, &gm)) { too_large(); break; }
+      if (!geometry(cfg, fst, max_len, tuple_cap, heap_mult, &gm, crec_ok)) { too_large(); break; }
       if (cfg.semantics == 1 && gm.kind != kLean) {
         std::fprintf(stderr, "[libfst_b200] eager semantics need finite non-negative weights (lean kernel)\n");
         too_large(); break;
@@ -283,10 +336,10 @@ class Engine {
       p.arena = static_cast<uint8_t*>(d_workspace_); p.arena_stride = gm.stride;
       p.hash_cap = gm.hash_cap; p.tuple_cap = gm.tuple_cap; p.heap_cap = gm.heap_cap; p.bag_cap = gm.bag_cap; p.exhaustive = cfg.exhaustive;
       p.dense = gm.dense ? 1u : 0u; p.tab_entries = gm.tab_entries;
-      if (gm.kind == kLean) {
-        const LeanLayout L = lean_layout((int)gm.G, gm.dense, gm.tab_entries, gm.tuple_cap, gm.heap_cap);
+      if (gm.kind == kLean || gm.kind == kWave) {
+        const LeanLayout L = lean_layout((int)gm.G, gm.dense, gm.tab_entries, gm.tuple_cap, gm.heap_cap, gm.crec);
         p.off_keyof = L.off_keyof; p.off_l0 = L.off_l0; p.off_chunks = L.off_chunks;
-        p.n1 = L.n1; p.smem_words = L.smem_words; p.dense_stride = fst->view.num_states * 2u;
+        p.n1 = L.n1; p.smem_words = gm.smem_per_group / 4; p.dense_stride = fst->view.num_states * 2u;
         p.key_sbits = 1; while ((1u << p.key_sbits) < p.dense_stride) p.key_sbits++;
         p.eager = cfg.semantics == 1 ? 1u : 0u;
       }
@@ -294,6 +347,7 @@ class Engine {
       p.pool_cursor = reinterpret_cast<unsigned long long*>(d_cnt + 2);
       p.relax_counter = reinterpret_cast<unsigned long long*>(d_cnt + 4);
       p.tuple_counter = reinterpret_cast<unsigned long long*>(d_cnt + 6);
+      p.wave_stats = reinterpret_cast<unsigned long long*>(d_cnt + 16);   // outside the 64 bytes reset per batch: cumulative
       p.status = d_status; p.path_len = d_path_len_; p.pool_off = d_pool_off_; p.final_w = d_final; p.n_tuples = d_ntuples;
       p.pool = d_pool_; p.pool_cap = pool_cap_;
       launch_search(gm, blocks, threads, p, stream);
@@ -301,16 +355,21 @@ class Engine {
       FSTB_CUDA(cudaGetLastError());
       // any string that overflowed its arena (or the pool)?
       FSTB_CUDA(cudaMemsetAsync(d_cnt + 1, 0, 4, stream));
-      FSTB_CUDA(cudaMemsetAsync(d_cnt + 9, 0, 4, stream));
-      collect_retry_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_status, n, d_order_buf_[pass & 1], d_cnt + 1, d_cnt + 9);
+      FSTB_CUDA(cudaMemsetAsync(d_cnt + 9, 0, 8, stream));
+      collect_retry_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_status, n, d_order_buf_[pass & 1], d_cnt + 1, d_cnt + 9, d_cnt + 10);
       bc->launches++;
       FSTB_CUDA(cudaMemcpyAsync(h_small_, d_cnt, 64, cudaMemcpyDeviceToHost, stream));
       FSTB_CUDA(cudaStreamSynchronize(stream));
       const uint32_t* hc = static_cast<const uint32_t*>(h_small_);
-      const uint32_t retry = hc[1], heap_retry = hc[9];
+      const uint32_t retry = hc[1], heap_retry = hc[9], wide_retry = hc[10];
+      if (std::getenv("LIBFST_B200_DEBUG")) {
+        unsigned long long ws[4] = {0, 0, 0, 0};
+        cudaMemcpy(ws, d_cnt + 16, 32, cudaMemcpyDeviceToHost);
+        if (gm.kind == kWave) std::fprintf(stderr, "[libfst_b200] wave stats (cumulative): chunk steps %llu, tuples popped by chunks %llu, single-pop steps %llu, abandoned chunks %llu\n", ws[0], ws[1], ws[2], ws[3]);
+      }
       if (std::getenv("LIBFST_B200_DEBUG"))
         std::fprintf(stderr, "[libfst_b200] pass %u kind %d G %u dense %d eager %d tuple_cap %u heap_cap %u items %u groups %u retry %u heap_retry %u\n",
-                     pass, gm.kind, gm.G, (int)gm.dense, (int)gm.eager, gm.tuple_cap, gm.heap_cap, n_items, blocks * gpb, retry, heap_retry);
+                     pass, gm.kind, gm.G, (int)gm.dense + (int)gm.crec, (int)gm.eager, gm.tuple_cap, gm.heap_cap, n_items, blocks * gpb, retry, heap_retry);
       unsigned long long pool_used; std::memcpy(&pool_used, hc + 2, 8);
       if (retry == 0) break;
       if (pool_used > pool_cap_) {
@@ -327,7 +386,8 @@ class Engine {
         heap_mult *= 4;
         if (heap_mult > fst->hint_heap_mult) fst->hint_heap_mult = heap_mult;
       }
-      if (retry > heap_retry) {
+      if (wide_retry > 0) { crec_ok = false; fst->crec_failed = true; }   // distances beyond 20 bits: 16-byte records from now on
+      if (retry > heap_retry + wide_retry) {
         if (gm.kind == kLean && gm.dense && gm.tuple_cap >= gm.tab_entries) { too_large(); break; }   // cannot happen: N <= records
         if (tuple_cap > (1u << 31) / 8) { too_large(); break; }
         tuple_cap *= 8;
@@ -538,21 +598,21 @@ class Engine {
 
   uint32_t init_launches_ = 0;
 
-  enum { kSerial = 0, kWarp = 1, kLean = 2 };
+  enum { kSerial = 0, kWarp = 1, kLean = 2, kWave = 3 };
   // Arena geometry of one pass: which kernel, and every capacity that shapes the arena.
   struct Geom {
-    int kind = kWarp; uint32_t G = 32; bool dense = false, slab = false, eager = false; uint64_t tab_entries = 0;
+    int kind = kWarp; uint32_t G = 32; bool dense = false, slab = false, eager = false, crec = false; uint64_t tab_entries = 0;
     uint32_t hash_cap = 0, tuple_cap = 0, heap_cap = 0, bag_cap = 0, smem_per_group = 0; uint64_t stride = 0;
     uint64_t off_l0 = 0, tab_bytes = 0, l0_bytes = 0;
     bool same(const Geom& o) const {
-      return kind == o.kind && G == o.G && dense == o.dense && slab == o.slab && tab_entries == o.tab_entries && hash_cap == o.hash_cap &&
+      return kind == o.kind && G == o.G && dense == o.dense && crec == o.crec && slab == o.slab && tab_entries == o.tab_entries && hash_cap == o.hash_cap &&
              tuple_cap == o.tuple_cap && heap_cap == o.heap_cap && bag_cap == o.bag_cap && stride == o.stride;
     }
   };
   static constexpr uint64_t kDenseLimitBytes = 96ull << 20;   // per-string dense table budget
   Geom layout_;
 
-  static bool geometry(const Config& cfg, const DeviceFst* fst, uint32_t max_len, uint32_t tuple_cap, uint32_t heap_mult, Geom* g) {
+  static bool geometry(const Config& cfg, const DeviceFst* fst, uint32_t max_len, uint32_t tuple_cap, uint32_t heap_mult, Geom* g, bool crec_ok = false) {
     *g = Geom();
     if (fst->serial) {
       g->kind = kSerial; g->G = choose_lanes(cfg, fst);
@@ -565,6 +625,10 @@ class Engine {
     }
     if (tuple_cap < 256) tuple_cap = 256;
     const bool lean = fst->lean_ok && cfg.engine != 1;
+    // wave kernel (one warp per string, a ready word per step): only on request — measured slower than the lean
+    // kernel on the bench transducers (their pop order keeps jumping back to old ids, chunks stay short)
+    const bool wave_forced = cfg.engine >= 4 && cfg.engine <= 6;
+    const bool wave = lean && fst->wave_ok && cfg.semantics == 0 && wave_forced;
     if (!lean) {
       if (tuple_cap > kMaxFastTuples) return false;
       g->kind = kWarp; g->G = 32; g->tuple_cap = tuple_cap;
@@ -577,17 +641,29 @@ class Engine {
     }
     g->kind = kLean;
     g->G = (cfg.lanes_per_string == 8 || cfg.lanes_per_string == 16 || cfg.lanes_per_string == 32) ? cfg.lanes_per_string : fst->lean_lanes;
-    g->slab = fst->view.slab_lanes == g->G;
+    if (wave) { g->kind = kWave; g->G = 32; }
+    g->slab = g->G == 8 ? fst->view.wslab != nullptr : fst->view.slab_lanes == g->G;
     g->eager = cfg.semantics == 1;
     const uint64_t E = (uint64_t)(max_len + 1) * fst->view.num_states * 2;
-    const bool dense_ok = E < 0xFFFFFF00ull && E * 16 <= kDenseLimitBytes;
+    // compact 8-byte records: lean kernel, lazy semantics, integer weights, ids below 2^22 - 1
+    const bool crec = crec_ok && !wave && cfg.semantics == 0 && std::min<uint64_t>(tuple_cap, E) < kCrecNone &&
+                      std::getenv("LIBFST_B200_NO_CREC") == nullptr;
+    const uint64_t rec_bytes = crec ? 8 : 16;
+    const bool dense_ok = E < 0xFFFFFF00ull && E * rec_bytes <= kDenseLimitBytes;
     // dense pays when the search touches a good part of the (position x state) grid; a small search keeps its
     // hash table in cache instead
     const uint64_t hash_bytes = (uint64_t)tuple_cap * 50;
-    g->dense = cfg.engine == 3 ? dense_ok : (cfg.engine == 2 ? false : dense_ok && (E * 16 <= 8 * hash_bytes || E * 16 <= (256u << 10)));
+    g->dense = (cfg.engine == 3 || cfg.engine == 6) ? dense_ok
+               : ((cfg.engine == 2 || cfg.engine == 5) ? false : dense_ok && (E * rec_bytes <= 8 * hash_bytes || E * rec_bytes <= (256u << 10)));
+    if (g->kind == kWave) {
+      // the arbitration key is the compact 32-bit tuple key (position << key_sbits | state << 1 | filter)
+      uint32_t sb = 1; while ((1ull << sb) < (uint64_t)fst->view.num_states * 2) sb++;
+      if (((uint64_t)(max_len + 1) << sb) > 0xFFFFFFF0ull) { g->kind = kLean; g->G = (cfg.lanes_per_string == 8 || cfg.lanes_per_string == 16 || cfg.lanes_per_string == 32) ? cfg.lanes_per_string : fst->lean_lanes; g->slab = g->G == 8 ? fst->view.wslab != nullptr : fst->view.slab_lanes == g->G; }
+    }
     if (g->dense) {
       if ((uint64_t)tuple_cap > E) tuple_cap = (uint32_t)E;
       g->tab_entries = E; g->hash_cap = 0;
+      g->crec = crec && g->kind == kLean;
     } else {
       g->hash_cap = (uint32_t)std::min<uint64_t>(0xFFFFFFF0ull, (uint64_t)tuple_cap * 100 / 65 + 16);
       g->tab_entries = g->hash_cap;
@@ -597,8 +673,8 @@ class Engine {
     // radix-heap pool (128-byte chunks of 31 ids): shallow until a search really needs distance levels
     g->heap_cap = 96 + (tuple_cap / 96) * heap_mult;
     g->bag_cap = 0;
-    LeanLayout L = lean_layout((int)g->G, g->dense, g->tab_entries, g->tuple_cap, g->heap_cap);
-    g->stride = L.total; g->smem_per_group = L.smem_words * 4;
+    LeanLayout L = lean_layout((int)g->G, g->dense, g->tab_entries, g->tuple_cap, g->heap_cap, g->crec);
+    g->stride = L.total; g->smem_per_group = (L.smem_words + (g->kind == kWave ? kWaveArbWords : 0u)) * 4;
     g->off_l0 = L.off_l0; g->tab_bytes = L.tab_bytes; g->l0_bytes = L.l0_bytes;
     return true;
   }
@@ -614,8 +690,9 @@ class Engine {
 
   template <int G, bool EAGER>
   static const void* lean_kernel_ptr_ge(const Geom& g) {
-    if (g.dense) return g.slab ? (const void*)csp_batch_lean_kernel<G, true, true, EAGER> : (const void*)csp_batch_lean_kernel<G, true, false, EAGER>;
-    return g.slab ? (const void*)csp_batch_lean_kernel<G, false, true, EAGER> : (const void*)csp_batch_lean_kernel<G, false, false, EAGER>;
+    if (!EAGER && g.crec) return g.slab ? (const void*)csp_batch_lean_kernel<G, 2, true, false> : (const void*)csp_batch_lean_kernel<G, 2, false, false>;
+    if (g.dense) return g.slab ? (const void*)csp_batch_lean_kernel<G, 1, true, EAGER> : (const void*)csp_batch_lean_kernel<G, 1, false, EAGER>;
+    return g.slab ? (const void*)csp_batch_lean_kernel<G, 0, true, EAGER> : (const void*)csp_batch_lean_kernel<G, 0, false, EAGER>;
   }
   template <int G>
   static const void* lean_kernel_ptr_g(const Geom& g) { return g.eager ? lean_kernel_ptr_ge<G, true>(g) : lean_kernel_ptr_ge<G, false>(g); }
@@ -625,6 +702,7 @@ class Engine {
   static const void* kernel_ptr(const Geom& g) {
     if (g.kind == kWarp) return (const void*)csp_batch_warp_kernel;
     if (g.kind == kLean) return lean_kernel_ptr(g);
+    if (g.kind == kWave) return g.dense ? (const void*)csp_batch_wave_kernel<true> : (const void*)csp_batch_wave_kernel<false>;
     switch (g.G) { case 32: return (const void*)csp_batch_kernel<32, true>; case 16: return (const void*)csp_batch_kernel<16, true>;
                    case 8: return (const void*)csp_batch_kernel<8, true>; default: return (const void*)csp_batch_kernel<4, true>; }
   }
@@ -646,9 +724,9 @@ class Engine {
   static void launch_search(const Geom& g, uint32_t blocks, uint32_t threads, const SearchParams& p, cudaStream_t s) {
     const size_t sm = (size_t)(threads / g.G) * g.smem_per_group;
     if (g.kind == kWarp) { csp_batch_warp_kernel<<<blocks, threads, sm, s>>>(p); return; }
-    if (g.kind == kLean) {
+    if (g.kind == kLean || g.kind == kWave) {
       void* args[] = {const_cast<SearchParams*>(&p)};
-      cudaLaunchKernel(lean_kernel_ptr(g), dim3(blocks), dim3(threads), args, sm, s);
+      cudaLaunchKernel(kernel_ptr(g), dim3(blocks), dim3(threads), args, sm, s);
       return;
     }
     switch (g.G) { case 32: csp_batch_kernel<32, true><<<blocks, threads, 0, s>>>(p); break; case 16: csp_batch_kernel<16, true><<<blocks, threads, 0, s>>>(p); break;
@@ -682,7 +760,7 @@ class Engine {
         warp_arena_init_kernel<<<blocks, 256, 0, s>>>(static_cast<uint8_t*>(d_workspace_), g.stride, groups, g.hash_cap, g.tuple_cap, g.heap_cap, g.bag_cap);
         init_launches_++;
         FSTB_CUDA(cudaGetLastError());
-      } else if (g.kind == kLean) {
+      } else if (g.kind == kLean || g.kind == kWave) {
         uint64_t vecs = (g.tab_bytes + g.l0_bytes) / 16 * groups;
         uint32_t blocks = (uint32_t)std::min<uint64_t>((vecs + 255) / 256, (uint64_t)sm_count * 32);
         lean_arena_init_kernel<<<blocks, 256, 0, s>>>(static_cast<uint8_t*>(d_workspace_), g.stride, groups, g.off_l0, g.tab_bytes, g.l0_bytes);

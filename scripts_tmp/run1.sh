@@ -1,5 +1,4 @@
 export LIBFST_B200_DEBUG=1
-timeout 120 python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --workload ambiguous --len 251 --semantics eager --batch 8 > gpurun_out/tmp.log 2>gpurun_out/tmp.err; echo rc=$?; tail -8 gpurun_out/tmp.err; cat gpurun_out/tmp.log | cut -c1-300
-unset LIBFST_B200_DEBUG
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-timeout 300 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/b96.log 2>gpurun_out/b96.err; echo rc=$?; tail -3 gpurun_out/b96.err; cut -c1-600 gpurun_out/b96.log
+for b in 14208 16576 37888; do
+timeout 300 python bench.py --steps 2 --warmup 2 --no-cpu-baseline --no-e2e --batch $b > gpurun_out/b96_$b.log 2>gpurun_out/b96_$b.err; echo rc=$?; tail -1 gpurun_out/b96_$b.err; cut -c1-200 gpurun_out/b96_$b.log
+done

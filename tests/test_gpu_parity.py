@@ -255,7 +255,7 @@ def test_cycle_hazard_is_reported(L, O, gpu):
     assert L.compose_frozen_shortest_path(L.MutableFst.compile_string(s), fprod, 1) is None   # reference: OOM -> invalid handle
 
 
-@pytest.mark.parametrize("engine,lanes", [(1, 0), (2, 32), (2, 16), (2, 8), (3, 32), (3, 16), (3, 8), (0, 0)])
+@pytest.mark.parametrize("engine,lanes", [(1, 0), (2, 32), (2, 16), (2, 8), (3, 32), (3, 16), (3, 8), (0, 0), (4, 0), (5, 0), (6, 0), (7, 0)])
 def test_engines_agree(L, O, gpu, engine, lanes):
     """Every kernel choice for byte-string batches (general warp kernel, lean + hash table, lean + dense table;
     32 or 16 lanes per string) must reproduce the oracle bit for bit, in early-exit and exhaustive mode."""
@@ -305,7 +305,7 @@ def test_lean_window_eviction_and_levels(L, O, gpu):
     fprod, forc, _ = frozen_pair(L, O, Spec(n, 0, [0.0 if rng.random() < 0.3 else None for _ in range(n)], arcs))
     strings = [bytes(rng.randint(0, 1) for _ in range(rng.randint(20, 60))) for _ in range(24)]
     try:
-        for engine, lanes in ((2, 32), (3, 32), (3, 16), (2, 16), (3, 8), (2, 8), (0, 0)):
+        for engine, lanes in ((2, 32), (3, 32), (3, 16), (2, 16), (3, 8), (2, 8), (0, 0), (5, 0), (6, 0)):
             for exhaustive in (1, 0):
                 L.configure(engine=engine, lanes_per_string=lanes, exhaustive=exhaustive)
                 res = assert_batch_matches_oracle(L, O, fprod, forc, strings)
@@ -376,3 +376,102 @@ def test_eager_semantics_config5(L, O, gpu, engine, lanes):
     finally:
         L.configure()
     assert differ > 0
+
+
+@pytest.mark.parametrize("engine", [0, 2])
+def test_eager_config5_full_length(L, O, gpu, engine):
+    """Config 5 at its literal size (label 1 x 251 against the ambiguous chain: 126 756 lattice states).  With the
+    hash table (engine 2) the adaptive passes go through a capacity where the search phase nearly fills the table
+    and the BFS phase meets new tuples on top of it — the table must report overflow, not fill up."""
+    from common import assert_batch_matches_eager_oracle
+    img = gen_image(O, 2, 4096, 12)
+    fprod, forc = L.Fst.from_image(img), O.Frozen.from_bytes(img)
+    strings = [bytes(251), bytes(250), bytes(160), bytes(251)]   # byte 0 = label 1
+    try:
+        L.configure(engine=engine, semantics=L.EAGER)
+        res = assert_batch_matches_eager_oracle(L, O, fprod, forc, strings)
+        assert res.n_tuples[0] == 126756
+    finally:
+        L.configure()
+
+
+@pytest.mark.parametrize("engine", [5, 6])
+def test_wave_kernel_tie_heavy(L, O, gpu, engine):
+    """Wave kernel (one warp per string, a ready word of up to 32 tuples per step, csp_wave.cuh): wide ready sets
+    with massive exact ties, several distance levels, tuples created above the level and lowered inside the same
+    chunk, existing tuples lowered to the level (chunk abandoned -> single pop), states wider than the wave slab."""
+    rng = random.Random(4242 + engine)
+    cases = []
+    for case in range(30):
+        n = rng.randint(8, 120)
+        nlab = rng.randint(1, 3)
+        wchoice = rng.choice([[0], [0, 0, 0, 1], [0, 1, 2, 3], [0, 0.5, 0.25, 1.5], [0, 0, 0, 0, 5]])
+        arcs = []
+        for s in range(n):
+            deg = rng.randint(1, 7) if case % 5 else rng.randint(1, 14)   # every fifth case has states wider than 8 records
+            for _ in range(deg):
+                il = 0 if rng.random() < 0.25 else rng.randint(1, nlab)
+                nxt = min(n - 1, s + rng.randint(0, 4)) if rng.random() < 0.8 else rng.randrange(n)
+                arcs.append((s, il, rng.randint(0, 3), float(rng.choice(wchoice)), nxt))
+        finals = [float(rng.choice(wchoice)) if rng.random() < 0.3 else None for _ in range(n)]
+        finals[n - 1] = 0.0
+        fprod, forc, _ = frozen_pair(L, O, Spec(n, 0, finals, arcs))
+        strings = [bytes(rng.randint(0, nlab - 1) for _ in range(rng.randint(0, 48))) for _ in range(24)]
+        cases.append((fprod, forc, strings))
+    try:
+        for exhaustive in (1, 0):
+            L.configure(engine=engine, exhaustive=exhaustive)
+            for fprod, forc, strings in cases:
+                res = assert_batch_matches_oracle(L, O, fprod, forc, strings)
+                if exhaustive:
+                    for i, s in enumerate(strings):
+                        p = O.csp_bytes(forc, s)
+                        if p.status == O.STATUS_OK:
+                            assert res.n_tuples[i] == p.tuples
+    finally:
+        L.configure()
+
+
+def test_wave_kernel_bench_shapes(L, O, gpu):
+    """The bench transducers through the wave kernel at sizes the oracle finishes quickly (dense and hash table)."""
+    try:
+        for engine in (6, 5):
+            L.configure(engine=engine)
+            for kind, lens in ((1, [0, 1, 5, 11, 19, 33]), (2, [0, 1, 11, 33, 96, 160]), (0, [7, 96])):
+                img = gen_image(O, kind, 4096 if kind != 1 else 1024, 12)
+                strings = [bytes(i % 12 for i in range(k)) if kind == 0 else bytes(k) for k in lens]
+                assert_batch_matches_oracle(L, O, L.Fst.from_image(img), O.Frozen.from_bytes(img), strings)
+    finally:
+        L.configure()
+
+
+def test_compact_records_and_wide_retry(L, O, gpu):
+    """Integer-weight transducers use 8-byte table records (dist:20 | id:22 | prev:22) in the dense lean kernel; a
+    distance beyond 20 bits sends the string back with 16-byte records (status stays PATH, output identical).
+    LIBFST_B200_NO_CREC=1 forces 16-byte records: both forms must agree with the oracle."""
+    import os
+    rng = random.Random(77)
+    n = 330
+    arcs = []
+    for s in range(n - 1):
+        arcs.append((s, 1, 1, 4000.0, s + 1))
+        arcs.append((s, 1, 2, 4095.0, s + 1))
+        if s % 3 == 0:
+            arcs.append((s, 0, 3, 7.0, s + 1))
+        arcs.append((s, 2, 2, float(rng.randint(0, 3)), min(n - 1, s + rng.randint(1, 2))))
+    fprod, forc, _ = frozen_pair(L, O, Spec(n, 0, [0.0] * n, arcs))
+    strings = [bytes(300), bytes(10), bytes([1] * 200), bytes(rng.randint(0, 1) for _ in range(280)), b""]
+    try:
+        for env in ("0", "1"):
+            os.environ["LIBFST_B200_NO_CREC"] = env
+            if env == "0":
+                del os.environ["LIBFST_B200_NO_CREC"]
+            for engine, lanes in ((3, 8), (3, 16), (0, 0)):
+                L.configure(engine=engine, lanes_per_string=lanes)
+                res = assert_batch_matches_oracle(L, O, fprod, forc, strings)
+                assert res.final_weights[0] == 0.0 and res.status[0] == L.PATH
+                il, ol, w = res.path(0)
+                assert float(np.sum(w)) > 1048575.0      # the first string's distance really outgrows 20 bits
+    finally:
+        os.environ.pop("LIBFST_B200_NO_CREC", None)
+        L.configure()
