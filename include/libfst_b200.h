@@ -203,6 +203,9 @@ typedef struct {
 FstError fst_b200_configure(const FstB200Config* cfg);
 /* Counters of the last batched call on this thread: kernels launched, relaxations. */
 void fst_b200_last_counters(uint32_t* launches, uint64_t* relaxations, double* device_ms);
+/* Strings the first search pass of the last batched call on this thread held in flight, and how many the device
+   can hold for that geometry (occupancy and workspace budget): a batch of `capacity` strings is one full wave. */
+void fst_b200_last_occupancy(uint32_t* resident, uint32_t* capacity);
 /* Number of usable CUDA devices (0 => every search call fails loudly). */
 int32_t fst_b200_device_count(void);
 const char* fst_b200_version(void);

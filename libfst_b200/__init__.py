@@ -85,6 +85,7 @@ EXPORTS = {
     "fst_b200_mutable_add_arcs": (C.c_int, [C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fst_b200_configure": (C.c_int, [C.POINTER(Config)]),
     "fst_b200_last_counters": (None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
+    "fst_b200_last_occupancy": (None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "fst_b200_device_count": (C.c_int32, []),
     "fst_b200_version": (C.c_char_p, []),
 }
@@ -133,6 +134,12 @@ def configure(workspace_bytes=0, lanes_per_string=0, tuples_hint=0, exhaustive=0
     rc = lib().fst_b200_configure(C.byref(cfg))
     if rc != FST_OK:
         raise ValueError(f"fst_b200_configure failed: {rc}")
+
+
+def last_occupancy():
+    a, b = C.c_uint32(0), C.c_uint32(0)
+    lib().fst_b200_last_occupancy(C.byref(a), C.byref(b))
+    return dict(resident=a.value, capacity=b.value)
 
 
 def last_counters():

@@ -616,6 +616,11 @@ FstError fst_b200_configure(const FstB200Config* cfg) {
   return FST_OK;
 }
 
+void fst_b200_last_occupancy(uint32_t* resident, uint32_t* capacity) {
+  if (resident) *resident = t_last.resident;
+  if (capacity) *capacity = t_last.capacity;
+}
+
 void fst_b200_last_counters(uint32_t* launches, uint64_t* relaxations, double* device_ms) {
   if (launches) *launches = t_last.launches;
   if (relaxations) *relaxations = t_last.relax;

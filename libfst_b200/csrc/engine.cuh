@@ -245,6 +245,8 @@ struct BatchCounters {
   double device_ms = 0;
   uint64_t path_total = 0, path_required = 0;
   uint32_t max_tuples = 0;
+  uint32_t resident = 0;     // strings searched concurrently by the first pass (arenas that fit the workspace budget)
+  uint32_t capacity = 0;     // ... and how many the device could hold for this geometry (min of occupancy and memory)
 };
 
 class Engine {
@@ -329,6 +331,7 @@ class Engine {
       }
       FSTB_CUDA(ensure_workspace(gm, blocks * gpb, stream));
       bc->launches += init_launches_; init_launches_ = 0;
+      if (pass == 0) { bc->resident = blocks * gpb; bc->capacity = std::min(max_groups, fit >= gpb ? (fit / gpb) * gpb : fit); }
 
       SearchParams p{};
       p.fst = fst->view;
@@ -382,7 +385,7 @@ class Engine {
       n_items = retry;
       d_order = d_order_buf_[pass & 1];
       if (heap_retry > 0) {
-        if (heap_mult >= 16) { too_large(); break; }
+        if (heap_mult >= 256) { too_large(); break; }
         heap_mult *= 4;
         if (heap_mult > fst->hint_heap_mult) fst->hint_heap_mult = heap_mult;
       }
@@ -671,7 +674,7 @@ class Engine {
     if (tuple_cap > kMaxFastTuples) return false;
     g->tuple_cap = tuple_cap;
     // radix-heap pool (128-byte chunks of 31 ids): shallow until a search really needs distance levels
-    g->heap_cap = 96 + (tuple_cap / 96) * heap_mult;
+    g->heap_cap = 96 + (tuple_cap / 384) * heap_mult;
     g->bag_cap = 0;
     LeanLayout L = lean_layout((int)g->G, g->dense, g->tab_entries, g->tuple_cap, g->heap_cap, g->crec);
     g->stride = L.total; g->smem_per_group = (L.smem_words + (g->kind == kWave ? kWaveArbWords : 0u)) * 4;

@@ -1,4 +1,2 @@
-export LIBFST_B200_DEBUG=1
-for b in 14208 16576 37888; do
-timeout 300 python bench.py --steps 2 --warmup 2 --no-cpu-baseline --no-e2e --batch $b > gpurun_out/b96_$b.log 2>gpurun_out/b96_$b.err; echo rc=$?; tail -1 gpurun_out/b96_$b.err; cut -c1-200 gpurun_out/b96_$b.log
-done
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+LIBFST_B200_DEBUG=1 timeout 600 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo rc=$?; grep -v "^\[libfst" gpurun_out/bench_default.err | tail -3; grep "pass 0" gpurun_out/bench_default.err | tail -1; cat gpurun_out/bench_default.json
