@@ -57,12 +57,15 @@ def parse():
     ap.add_argument("--semantics", default="lazy", choices=["lazy", "eager"],
                     help="lazy = fst_compose_frozen_shortest_path (headline); eager = compose then shortest_path (config 5)")
     ap.add_argument("--engine", type=int, default=0, help="0 auto, 1 general warp kernel, 2 lean+hash, 3 lean+dense")
+    ap.add_argument("--mixed", action="store_true",
+                    help="lengths drawn uniformly from the issue #1 profile list {11..251} (seed 1) instead of --len: load balance")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="strings in the CPU baseline sample (0 = auto)")
     return ap.parse_args()
 
 
+MIXED_LENS = [11, 19, 33, 64, 96, 128, 160, 192, 224, 251]   # bench/run_issue1_profile_bench.py:24-25
 DEFAULT_BATCH = {"epsilon_dense": 9472, "ambiguous": 65536, "plain": 1 << 20, "wetext": 1 << 18}   # eps-dense: 64 strings per SM in flight
 
 
@@ -80,6 +83,11 @@ def workload_strings(args, batch, seed, sources=None):
         lens = np.fromiter((len(x) for x in strings), np.uint64, len(strings))
         offsets = np.zeros(batch + 1, np.uint64); np.cumsum(lens, out=offsets[1:])
         data = np.frombuffer(b"".join(strings), np.uint8).copy()
+    elif getattr(args, "mixed", False):
+        lens = np.random.default_rng(seed).choice(np.array(MIXED_LENS, np.uint64), batch)
+        offsets = np.zeros(batch + 1, np.uint64); np.cumsum(lens, out=offsets[1:])
+        full = np.frombuffer(input_string(args.workload, max(MIXED_LENS), args.branches), np.uint8)
+        data = np.concatenate([full[:int(n)] for n in lens]) if batch else np.zeros(0, np.uint8)
     else:
         s = input_string(args.workload, args.len, args.branches)
         data = np.frombuffer(s * batch, np.uint8) if len(s) else np.zeros(0, np.uint8)
@@ -201,7 +209,7 @@ def run_reference(args):
 def workload_config(args, batch, state_bytes, resident=None):
     desc = (f"{SCENARIO[args.workload]} dict={args.dict} len=U[11,251] (70% dictionary words, 30% printable bytes)"
             if args.workload == "wetext" else
-            f"{SCENARIO[args.workload]} len={args.len} transducer_len={args.transducer_len} branches={args.branches}")
+            f"{SCENARIO[args.workload]} len={'mixed U{11,19,33,64,96,128,160,192,224,251} seed 1' if getattr(args, 'mixed', False) else args.len} transducer_len={args.transducer_len} branches={args.branches}")
     if args.semantics == "eager":
         desc = desc.replace("compose_frozen_lazy_shortest_path", "compose_frozen") + " + shortest_path (eager lattice, config 5)"
     return {"workload": desc, "semantics": args.semantics,
@@ -253,7 +261,7 @@ def main():
         for _ in range(2):
             r = L.compose_frozen_shortest_path_batch(fst, data, offsets)
         cap = max(296, L.last_occupancy()["capacity"])
-        waves = 1 if float(r.n_tuples.mean()) >= 100000 else 8
+        waves = 4 if args.mixed else (1 if float(r.n_tuples.mean()) >= 100000 else 8)
         batch = min(cap * waves, 1 << 20)
         data, offsets, max_len = workload_strings(args, batch, rank + 1)
     nbytes = int(offsets[-1])
