@@ -150,6 +150,17 @@ FstError fst_compose_frozen_shortest_path_batch(FstHandle b, const uint8_t* byte
                                                 uint32_t n_strings, FstB200BatchResult** out);
 void fst_b200_batch_free(FstB200BatchResult* r);
 
+/* Two-stage pipeline on the device (the reference's ITN flow README.md:177-189: per utterance
+ * fst_compile_string -> fst_compose_frozen_shortest_path(tagger) -> fst_print_output_string -> fst_compile_string
+ * -> fst_compose_frozen_shortest_path(verbalizer), src/c-api.zig:744-811, :1334-1372).  Stage 2 reads the
+ * output-tape strings of stage 1 straight from HBM.  The result describes stage 2 (paths, output bytes,
+ * final weights of the second composition); a string stage 1 could not transduce keeps stage 1's status
+ * (FST_B200_NO_PATH, ...) and an empty path.  Counters (tuples, relaxations, launches, device_ms) are sums of
+ * both stages.  Same error conventions as the batch entry. */
+FstError fst_compose_frozen_shortest_path_pipeline(FstHandle first, FstHandle second, const uint8_t* bytes,
+                                                   const uint64_t* offsets, uint32_t n_strings,
+                                                   FstB200BatchResult** out);
+
 /* Device-resident batch (inputs already in HBM; used for kernel-level timing and
  * for callers that keep a pipeline on the GPU).  All pointers are DEVICE pointers
  * on the current device; the call is asynchronous on `stream` (a cudaStream_t)

@@ -75,6 +75,8 @@ EXPORTS = {
     "fst_print_string": (C.c_int32, [C.c_uint64, C.POINTER(C.c_uint8), C.c_uint32]),
     "fst_print_output_string": (C.c_int32, [C.c_uint64, C.POINTER(C.c_uint8), C.c_uint32]),
     "fst_teardown": (None, []),
+    "fst_compose_frozen_shortest_path_pipeline": (C.c_int, [C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32,
+                                                            C.POINTER(C.POINTER(_BatchResult))]),
     "fst_compose_frozen_shortest_path_batch": (C.c_int, [C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32,
                                                          C.POINTER(C.POINTER(_BatchResult))]),
     "fst_b200_batch_free": (None, [C.POINTER(_BatchResult)]),
@@ -313,14 +315,22 @@ def pack_strings(strings):
     return data, offsets
 
 
-def compose_frozen_shortest_path_batch(b: Fst, data: np.ndarray, offsets: np.ndarray, copy: bool = True) -> BatchResult:
-    """fst_compose_frozen_shortest_path_batch over host buffers."""
+def compose_frozen_shortest_path_pipeline(first: Fst, second: Fst, data: np.ndarray, offsets: np.ndarray) -> BatchResult:
+    """fst_compose_frozen_shortest_path_pipeline: first then second (tagger then verbalizer) without leaving the device."""
+    return compose_frozen_shortest_path_batch(first, data, offsets, second=second)
+
+
+def compose_frozen_shortest_path_batch(b: Fst, data: np.ndarray, offsets: np.ndarray, copy: bool = True, second: Fst = None) -> BatchResult:
+    """fst_compose_frozen_shortest_path_batch over host buffers (`second`: the two-stage pipeline entry)."""
     data = np.ascontiguousarray(data, np.uint8)
     offsets = np.ascontiguousarray(offsets, np.uint64)
     n = len(offsets) - 1
     keep = data if data.size else np.zeros(1, np.uint8)
     out = C.POINTER(_BatchResult)()
-    rc = lib().fst_compose_frozen_shortest_path_batch(b.h, keep.ctypes.data, offsets.ctypes.data, n, C.byref(out))
+    if second is None:
+        rc = lib().fst_compose_frozen_shortest_path_batch(b.h, keep.ctypes.data, offsets.ctypes.data, n, C.byref(out))
+    else:
+        rc = lib().fst_compose_frozen_shortest_path_pipeline(b.h, second.h, keep.ctypes.data, offsets.ctypes.data, n, C.byref(out))
     if rc != FST_OK:
         raise RuntimeError(f"fst_compose_frozen_shortest_path_batch failed: FstError {rc}")
     r = out.contents

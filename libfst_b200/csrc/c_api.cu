@@ -471,17 +471,22 @@ static int32_t map_status(int32_t s) {
                case kStInternal: return FST_B200_INTERNAL; default: return FST_B200_TOO_LARGE; }
 }
 
-FstError fst_compose_frozen_shortest_path_batch(FstHandle b, const uint8_t* bytes, const uint64_t* offsets,
-                                                uint32_t n_strings, FstB200BatchResult** out) {
+// Host-buffer batch against one transducer (b2 == FST_INVALID_HANDLE) or the two-stage pipeline b then b2.
+static FstError host_batch(FstHandle b, FstHandle b2, const uint8_t* bytes, const uint64_t* offsets,
+                           uint32_t n_strings, FstB200BatchResult** out) {
   if (!out) return FST_INVALID_ARG;
   *out = nullptr;
   if (!offsets || (!bytes && n_strings && offsets[n_strings] > 0)) return FST_INVALID_ARG;
   for (uint32_t i = 0; i < n_strings; i++) if (offsets[i + 1] < offsets[i]) return FST_INVALID_ARG;
-  FrozenEntry* fb;
+  const bool two = b2 != FST_INVALID_HANDLE;
+  FrozenEntry *fb, *fb2 = nullptr;
   { std::lock_guard<std::mutex> lk(g_mu); fb = g_frozen.pin(b); }
   if (!fb) return FST_INVALID_ARG;
   PinGuard pg{b};
-  if (fb->host->has_nan) return FST_INVALID_ARG;
+  if (two) { std::lock_guard<std::mutex> lk(g_mu); fb2 = g_frozen.pin(b2); }
+  if (two && !fb2) return FST_INVALID_ARG;
+  PinGuard pg2{two ? b2 : FST_INVALID_HANDLE};
+  if (fb->host->has_nan || (two && fb2->host->has_nan)) return FST_INVALID_ARG;
   if (!device_available()) {
     std::fprintf(stderr, "[libfst_b200] no CUDA device: the batched search has no CPU fallback\n");
     return FST_INVALID_STATE;
@@ -491,6 +496,8 @@ FstError fst_compose_frozen_shortest_path_batch(FstHandle b, const uint8_t* byte
   if (!en) return FST_INVALID_STATE;
   DeviceFst* img = fb->image_for(en->device, &err);
   if (!img) return err == cudaErrorMemoryAllocation ? FST_OOM : FST_INVALID_STATE;
+  DeviceFst* img2 = two ? fb2->image_for(en->device, &err) : nullptr;
+  if (two && !img2) return err == cudaErrorMemoryAllocation ? FST_OOM : FST_INVALID_STATE;
 
   const uint64_t nbytes = n_strings ? offsets[n_strings] - offsets[0] : 0;
   uint64_t max_len = 0;
@@ -523,6 +530,31 @@ FstError fst_compose_frozen_shortest_path_batch(FstHandle b, const uint8_t* byte
     const uint64_t need = std::max<uint64_t>(bc.path_required, bc.path_total);
     if (need > path_cap && attempt < 4) { path_cap = need + need / 4 + 1024; free_dev(); continue; }
     break;
+  }
+  if (two) {
+    // stage 2: the output-tape strings of stage 1 (still in HBM) are the inputs; strings stage 1 could not
+    // transduce keep stage 1's status.  Per string this is compile_string -> compose_frozen_shortest_path(b) ->
+    // print_output_string -> compile_string -> compose_frozen_shortest_path(b2) of the reference's ITN flow
+    // (README.md:177-189) without leaving the device.
+    const int32_t* d_status1 = d_status;
+    const uint8_t* d_in2 = d_obytes; const uint64_t* d_off2 = d_ooff;
+    uint64_t nbytes2 = 0; uint32_t max_len2 = 0;
+    if (n) cudaMemcpy(&nbytes2, d_ooff + n, 8, cudaMemcpyDeviceToHost);
+    if (en->last_max_out_len(n, stream, &max_len2) != cudaSuccess) return FST_INVALID_STATE;
+    const BatchCounters bc1 = bc;
+    path_cap = 2 * nbytes2 + 16ull * n + 1024;
+    for (int attempt = 0;; attempt++) {
+      if (en->ensure_io(n, 0, path_cap, 1) != cudaSuccess) { cudaGetLastError(); return FST_OOM; }
+      const Engine::IoBuffers& io = en->io(1);
+      d_status = io.status; d_poff = io.path_offsets; d_il = io.il; d_ol = io.ol; d_w = io.w;
+      d_fin = io.final_w; d_nt = io.n_tuples; d_ooff = io.out_offsets; d_obytes = io.out_bytes;
+      err = en->run_batch(img2, d_in2, d_off2, n, max_len2, d_status, d_poff, d_il, d_ol, d_w, d_fin, d_nt, path_cap, d_ooff, d_obytes, path_cap, stream, &bc, d_status1);
+      if (err != cudaSuccess) return err == cudaErrorMemoryAllocation ? FST_OOM : FST_INVALID_STATE;
+      const uint64_t need = std::max<uint64_t>(bc.path_required, bc.path_total);
+      if (need > path_cap && attempt < 4) { path_cap = need + need / 4 + 1024; continue; }
+      break;
+    }
+    bc.launches += bc1.launches; bc.passes += bc1.passes; bc.relax += bc1.relax; bc.tuples += bc1.tuples; bc.device_ms += bc1.device_ms;
   }
   t_last = bc;
   // assemble the pinned host result
@@ -572,6 +604,17 @@ FstError fst_compose_frozen_shortest_path_batch(FstHandle b, const uint8_t* byte
   r->pub.passes = bc.passes;
   *out = &r->pub;
   return FST_OK;
+}
+
+FstError fst_compose_frozen_shortest_path_batch(FstHandle b, const uint8_t* bytes, const uint64_t* offsets,
+                                                uint32_t n_strings, FstB200BatchResult** out) {
+  return host_batch(b, FST_INVALID_HANDLE, bytes, offsets, n_strings, out);
+}
+
+FstError fst_compose_frozen_shortest_path_pipeline(FstHandle first, FstHandle second, const uint8_t* bytes, const uint64_t* offsets,
+                                                   uint32_t n_strings, FstB200BatchResult** out) {
+  if (second == FST_INVALID_HANDLE) { if (out) *out = nullptr; return FST_INVALID_ARG; }
+  return host_batch(first, second, bytes, offsets, n_strings, out);
 }
 
 void fst_b200_batch_free(FstB200BatchResult* r) {

@@ -565,8 +565,9 @@ __global__ void __launch_bounds__(128) csp_batch_kernel(SearchParams p) {
     if (item >= p.n_items) break;
     uint32_t idx = p.order ? p.order[item] : item;
     LhsBytes lhs; lhs.s = p.bytes + p.offsets[idx]; lhs.len = (uint32_t)(p.offsets[idx + 1] - p.offsets[idx]);
-    uint32_t plen; uint64_t poff; double fw; uint32_t nt; unsigned long long nr;
-    int32_t status = search_one<G, SERIAL>(g, p, lhs, a, &plen, &poff, &fw, &nt, &nr);
+    uint32_t plen = 0; uint64_t poff = 0; double fw = d_inf(); uint32_t nt = 0; unsigned long long nr = 0;
+    const int32_t pre = p.skip ? p.skip[idx] : kStPath;   // an earlier pipeline stage failed: pass its status through
+    int32_t status = pre != kStPath ? pre : search_one<G, SERIAL>(g, p, lhs, a, &plen, &poff, &fw, &nt, &nr);
     if (g.lane == 0) {
       p.status[idx] = status; p.path_len[idx] = plen; p.pool_off[idx] = poff; p.final_w[idx] = fw; p.n_tuples[idx] = nt;
     }

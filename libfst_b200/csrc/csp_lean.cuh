@@ -965,8 +965,9 @@ __global__ void __launch_bounds__(128, FSTB_LEAN_MINBLOCKS) csp_batch_lean_kerne
       } else {
         idx = p.order ? p.order[item] : item;
         lhs.s = p.bytes + p.offsets[idx]; lhs.len = (uint32_t)(p.offsets[idx + 1] - p.offsets[idx]);
-        if (p.fst.start == kNone) {
-          if (g.lane == 0) { p.status[idx] = kStNoPath; p.path_len[idx] = 0; p.pool_off[idx] = 0; p.final_w[idx] = d_inf(); p.n_tuples[idx] = 0; }
+        const int32_t pre = p.skip ? p.skip[idx] : kStPath;
+        if (p.fst.start == kNone || pre != kStPath) {
+          if (g.lane == 0) { p.status[idx] = pre != kStPath ? pre : kStNoPath; p.path_len[idx] = 0; p.pool_off[idx] = 0; p.final_w[idx] = d_inf(); p.n_tuples[idx] = 0; }
         } else {
           lean_begin<G, DENSE>(p, g, c, st);
           phase = kRun; steps = 0;

@@ -295,8 +295,9 @@ __global__ void __launch_bounds__(128, 4) csp_batch_wave_kernel(const __grid_con
     if (item >= p.n_items) break;
     const uint32_t idx = p.order ? p.order[item] : item;
     LhsBytes lhs; lhs.s = p.bytes + p.offsets[idx]; lhs.len = (uint32_t)(p.offsets[idx + 1] - p.offsets[idx]);
-    if (p.fst.start == kNone) {
-      if (g.lane == 0) { p.status[idx] = kStNoPath; p.path_len[idx] = 0; p.pool_off[idx] = 0; p.final_w[idx] = d_inf(); p.n_tuples[idx] = 0; }
+    const int32_t pre = p.skip ? p.skip[idx] : kStPath;
+    if (p.fst.start == kNone || pre != kStPath) {
+      if (g.lane == 0) { p.status[idx] = pre != kStPath ? pre : kStNoPath; p.path_len[idx] = 0; p.pool_off[idx] = 0; p.final_w[idx] = d_inf(); p.n_tuples[idx] = 0; }
       continue;
     }
     lean_begin<32, DENSE>(p, g, c, st);

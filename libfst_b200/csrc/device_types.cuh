@@ -83,6 +83,8 @@ struct SearchParams {
   const uint8_t* bytes;
   const uint64_t* offsets;
   const uint32_t* order;   // optional: work item i -> string index (retry passes); null = identity
+  const int32_t* skip;     // optional: per-string status of an earlier pipeline stage; anything but kStPath is passed
+                           // through as this string's status and the string is not searched
   uint32_t n_items;
   // or: one general left operand (n_items == 1, bytes == nullptr)
   DevLhsCsr lhs;

@@ -291,7 +291,7 @@ class Engine {
                         int32_t* d_status, uint64_t* d_path_offsets, uint32_t* d_il, uint32_t* d_ol, double* d_w,
                         double* d_final, uint32_t* d_ntuples, uint64_t path_capacity,
                         uint64_t* d_out_offsets, uint8_t* d_out_bytes, uint64_t out_capacity,
-                        cudaStream_t stream, BatchCounters* bc) {
+                        cudaStream_t stream, BatchCounters* bc, const int32_t* d_skip = nullptr) {
     *bc = BatchCounters();
     if (n == 0) {
       FSTB_CUDA(cudaMemsetAsync(d_path_offsets, 0, 8, stream));
@@ -350,7 +350,7 @@ class Engine {
 
       SearchParams p{};
       p.fst = fst->view;
-      p.bytes = d_bytes; p.offsets = d_offsets; p.order = d_order; p.n_items = n_items;
+      p.bytes = d_bytes; p.offsets = d_offsets; p.order = d_order; p.n_items = n_items; p.skip = d_skip;
       p.arena = static_cast<uint8_t*>(d_workspace_); p.arena_stride = gm.stride;
       p.hash_cap = gm.hash_cap; p.tuple_cap = gm.tuple_cap; p.heap_cap = gm.heap_cap; p.bag_cap = gm.bag_cap; p.exhaustive = cfg.exhaustive;
       p.dense = gm.dense ? 1u : 0u; p.tab_entries = gm.tab_entries;
@@ -560,8 +560,10 @@ class Engine {
     uint64_t* out_offsets = nullptr; uint8_t* out_bytes = nullptr;
     uint64_t cap_n = 0, cap_bytes = 0, cap_path = 0;
   };
-  const IoBuffers& io() const { return io_; }
-  cudaError_t ensure_io(uint32_t n, uint64_t nbytes, uint64_t path_cap) {
+  const IoBuffers& io(int set = 0) const { return io_sets_[set]; }
+  // set 0: the batch entry (and stage 1 of the pipeline entry); set 1: stage 2 of the pipeline entry
+  cudaError_t ensure_io(uint32_t n, uint64_t nbytes, uint64_t path_cap, int set = 0) {
+    IoBuffers& io_ = io_sets_[set];
     if (n > io_.cap_n) {
       cudaFree(io_.offsets); cudaFree(io_.status); cudaFree(io_.path_offsets); cudaFree(io_.final_w); cudaFree(io_.n_tuples); cudaFree(io_.out_offsets);
       io_.offsets = nullptr; io_.status = nullptr; io_.path_offsets = nullptr; io_.final_w = nullptr; io_.n_tuples = nullptr; io_.out_offsets = nullptr;
@@ -590,17 +592,28 @@ class Engine {
   }
 
   void release_all() {
-    cudaFree(io_.bytes); cudaFree(io_.offsets); cudaFree(io_.status); cudaFree(io_.path_offsets); cudaFree(io_.il); cudaFree(io_.ol);
-    cudaFree(io_.w); cudaFree(io_.final_w); cudaFree(io_.n_tuples); cudaFree(io_.out_offsets); cudaFree(io_.out_bytes);
-    io_ = IoBuffers();
+    for (IoBuffers& io_ : io_sets_) {
+      cudaFree(io_.bytes); cudaFree(io_.offsets); cudaFree(io_.status); cudaFree(io_.path_offsets); cudaFree(io_.il); cudaFree(io_.ol);
+      cudaFree(io_.w); cudaFree(io_.final_w); cudaFree(io_.n_tuples); cudaFree(io_.out_offsets); cudaFree(io_.out_bytes);
+      io_ = IoBuffers();
+    }
     cudaFree(d_workspace_); d_workspace_ = nullptr; workspace_bytes_ = 0; layout_groups_ = 0; budget_cache_ = 0;
     free_scratch();
   }
 
   uint64_t pool_capacity() const { return pool_cap_; }
 
+  // Longest output-tape string of the last run_batch that produced output bytes (pipeline: stage 2's max_len).
+  cudaError_t last_max_out_len(uint32_t n, cudaStream_t stream, uint32_t* out) {
+    uint32_t* d_cnt = static_cast<uint32_t*>(d_small_);
+    FSTB_CUDA(cudaMemsetAsync(d_cnt + 11, 0, 4, stream));
+    if (n) max_u32_kernel<<<std::min<uint32_t>((n + 255) / 256, 592), 256, 0, stream>>>(d_out_len_, n, d_cnt + 11);
+    FSTB_CUDA(cudaMemcpyAsync(out, d_cnt + 11, 4, cudaMemcpyDeviceToHost, stream));
+    return cudaStreamSynchronize(stream);
+  }
+
  private:
-  IoBuffers io_;
+  IoBuffers io_sets_[2];
   void* d_small_ = nullptr; void* h_small_ = nullptr;
   cudaEvent_t ev0_{}, ev1_{};
   // workspace (arenas)

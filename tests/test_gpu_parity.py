@@ -475,3 +475,56 @@ def test_compact_records_and_wide_retry(L, O, gpu):
     finally:
         os.environ.pop("LIBFST_B200_NO_CREC", None)
         L.configure()
+
+
+def test_two_stage_pipeline(L, O, gpu):
+    """tagger then verbalizer on the device == two oracle searches chained through the output tape
+    (compile_string -> composeShortestPath -> printStringFromTape -> compile_string -> composeShortestPath)."""
+    rng = random.Random(31337)
+    for case in range(12):
+        a = random_rhs(rng, max_states=7, nlab=3, real=(case % 3 == 1))
+        b = random_rhs(rng, max_states=7, nlab=3, real=(case % 3 == 2))
+        fa, oa, _ = frozen_pair(L, O, a)
+        fb, ob, _ = frozen_pair(L, O, b)
+        strings = [random_string(rng, nlab=3, max_len=10) for _ in range(60)]
+        data, offsets = L.pack_strings(strings)
+        res = L.compose_frozen_shortest_path_pipeline(fa, fb, data, offsets)
+        n_ok = 0
+        for i, s in enumerate(strings):
+            p1 = O.csp_bytes(oa, s)
+            if p1.status == O.STATUS_BACKTRACK_CYCLE:
+                assert res.status[i] == L.CYCLE, (case, i, s)
+                continue
+            if p1.status == O.STATUS_EMPTY:
+                assert res.status[i] == L.NO_PATH and len(res.path(i)[0]) == 0, (case, i, s, res.status[i])
+                continue
+            mid = p1.output_bytes()
+            # output labels of random transducers are 1..nlab -> bytes 0..nlab-1: valid second-stage inputs
+            p2 = O.csp_bytes(ob, mid)
+            if p2.status == O.STATUS_BACKTRACK_CYCLE:
+                assert res.status[i] == L.CYCLE, (case, i, s)
+                continue
+            if p2.status == O.STATUS_EMPTY:
+                assert res.status[i] == L.NO_PATH, (case, i, s, mid, res.status[i])
+                continue
+            assert res.status[i] == L.PATH, (case, i, s, mid, res.status[i])
+            il, ol, w = res.path(i)
+            assert np.array_equal(il, p2.ilabels) and np.array_equal(ol, p2.olabels), (case, i, s, mid)
+            assert np.array_equal(w.view(np.uint64), p2.weights.view(np.uint64))
+            assert np.float64(res.final_weights[i]).view(np.uint64) == np.float64(p2.final_weight).view(np.uint64)
+            assert res.output(i) == p2.output_bytes()
+            n_ok += 1
+        assert n_ok > 0 or case > 0
+    # the bench transducers chained: plain then plain (deterministic relabelling twice)
+    img = gen_image(O, 0, 512, 12)
+    f, o = L.Fst.from_image(img), O.Frozen.from_bytes(img)
+    strings = [bytes(i % 12 for i in range(k)) for k in (0, 1, 7, 40)]
+    data, offsets = L.pack_strings(strings)
+    res = L.compose_frozen_shortest_path_pipeline(f, f, data, offsets)
+    for i, s in enumerate(strings):
+        p1 = O.csp_bytes(o, s)
+        p2 = O.csp_bytes(o, p1.output_bytes()) if p1.status == O.STATUS_OK else None
+        if p2 is not None and p2.status == O.STATUS_OK:
+            assert res.status[i] == L.PATH and res.output(i) == p2.output_bytes()
+        else:
+            assert res.status[i] == L.NO_PATH
