@@ -205,9 +205,10 @@ __device__ __forceinline__ uint2 lean_ld_rec8(const uint8_t* q) {
 // transducers whose weights are all small non-negative integers (every distance is then an integer, exact in
 // both forms): half the table bytes per string, so more strings fit HBM and a DRAM sector holds four records.
 // All-ones = never touched in every kind.  A distance that does not fit 20 bits marks the string for a retry with
-// 16-byte records (LeanState::wide).
+// 16-byte records (LeanState::wide).  Kind 3 = kind 2 for the EAGER kernels (one id bit holds the BFS flag).
 constexpr uint32_t kCrecNone = 0x3FFFFFu;          // 22-bit id / prev: none
-constexpr double kCrecMaxDist = 1048575.0;         // 20-bit distance
+constexpr double kCrecMaxDist = 1048574.0;         // 20-bit distance; 0xFFFFF = +inf (a lattice state the search never reached, eager BFS)
+constexpr uint32_t kCrecBfsBit = 0x200000u;        // table kind 3 (eager): bit 21 of the id field = numbered by the BFS phase, ids < 2^21 - 1
 
 template <int DENSE>
 __device__ __forceinline__ void lean_keyof_store(const SearchParams& p, const LeanCtx& c, uint32_t id, uint32_t P, uint32_t SF) {
@@ -237,12 +238,13 @@ __device__ __forceinline__ uint32_t lean_dense_pos(const SearchParams& p, uint32
 template <int DENSE>
 __device__ __forceinline__ void lean_lookup(const SearchParams& p, const LeanCtx& c, uint32_t P, uint32_t SF, uint32_t& pos, double& dist,
                                             uint32_t& id, uint32_t& prev) {
-  if (DENSE == 2) {
+  if (DENSE >= 2) {
     pos = lean_dense_pos(p, P, SF);
     const uint2 v = lean_ld_rec8(c.base + (uint64_t)pos * 8);   // x = low word: id:10 low bits | prev:22 ; y = dist:20 | id:12 high bits
     const uint32_t i = ((v.y & 0xFFFu) << 10) | (v.x >> 22), pr = v.x & kCrecNone;
-    id = i == kCrecNone ? kNone : i; prev = pr == kCrecNone ? kNone : pr;
-    dist = i == kCrecNone ? d_inf() : (double)(v.y >> 12);
+    id = i == kCrecNone ? kNone : (DENSE == 3 ? ((i & (kCrecBfsBit - 1u)) | ((i & kCrecBfsBit) ? kBfsFlag : 0u)) : i);
+    prev = pr == kCrecNone ? kNone : pr;
+    dist = (i == kCrecNone || (v.y >> 12) == 0xFFFFFu) ? d_inf() : (double)(v.y >> 12);
   } else if (DENSE) {
     pos = lean_dense_pos(p, P, SF);
     const uint4 v = *reinterpret_cast<const uint4*>(c.base + (uint64_t)pos * 16);
@@ -282,9 +284,10 @@ __device__ __forceinline__ uint32_t lean_claim(const SearchParams& p, const Lean
 // sector consistent with what later plain-load probes must see (the claiming CAS acts on L2 only).
 template <int DENSE>
 __device__ __forceinline__ void lean_store(const LeanCtx& c, uint32_t pos, uint32_t P, uint32_t SF, double dist, uint32_t id, uint32_t prev) {
-  if (DENSE == 2) {
-    const uint32_t d = __double2uint_rn(fmin(dist, kCrecMaxDist)), pr = prev & kCrecNone;   // kNone -> kCrecNone
-    *reinterpret_cast<uint2*>(c.base + (uint64_t)pos * 8) = make_uint2((id << 22) | pr, (d << 12) | ((id >> 10) & 0xFFFu));
+  if (DENSE >= 2) {
+    const uint32_t d = d_isinf(dist) ? 0xFFFFFu : __double2uint_rn(fmin(dist, kCrecMaxDist)), pr = prev & kCrecNone;   // kNone -> kCrecNone
+    const uint32_t i = DENSE == 3 ? ((id & (kCrecBfsBit - 1u)) | ((id & kBfsFlag) ? kCrecBfsBit : 0u)) : id;
+    *reinterpret_cast<uint2*>(c.base + (uint64_t)pos * 8) = make_uint2((i << 22) | pr, (d << 12) | ((i >> 10) & 0xFFFu));
     return;
   }
   const uint4 v = make_uint4((uint32_t)__double2loint(dist), (uint32_t)__double2hiint(dist), id, prev);
@@ -564,7 +567,7 @@ __device__ __forceinline__ void lean_relax(const SearchParams& p, const Group<G>
   if (active) lean_lookup<DENSE>(p, c, P, SF, pos, old_dist, old_id, old_prev);
   // smallest new distance over the parallel arcs (fl(c + w) is monotone in w)
   const double nd = (bfs ? bfs_dist : __longlong_as_double((long long)st.last)) + wmin;
-  if (DENSE == 2 && active && nd > kCrecMaxDist) st.wide = true;
+  if (DENSE >= 2 && active && !bfs && nd > kCrecMaxDist) st.wide = true;   // (BFS phase: distances are final, +inf = unreached)
   const bool untouched = active && old_id == kNone;
   // search: a target is new when it has no record; BFS: when it has no BFS number yet (compose.zig:77-91)
   const bool is_new = bfs ? (active && (untouched || !(old_id & kBfsFlag))) : untouched;
@@ -831,7 +834,7 @@ __device__ __forceinline__ int32_t lean_finish(const SearchParams& p, const Grou
   const bool have_best = cold[kcHaveBest] != 0;
   const uint32_t best_id = cold[kcBestId];
   const double best_fw = __hiloint2double((int)cold[kcBestFwHi], (int)cold[kcBestFwLo]);
-  const bool wide = DENSE == 2 && g.any(st.wide);
+  const bool wide = DENSE >= 2 && g.any(st.wide);
   if (wide) {
     status = kStRetryWide;
   } else if (st.stuck) {
@@ -892,19 +895,19 @@ __device__ __forceinline__ int32_t lean_finish(const SearchParams& p, const Grou
   const bool mixed = st.bfs_started && aborted;   // id -> key array is part search ids, part BFS numbers
   if (mixed) {
     uint4* t = reinterpret_cast<uint4*>(c.base);
-    const uint64_t vecs = DENSE == 2 ? (p.tab_entries + 1) / 2 : p.tab_entries * (DENSE ? 1ull : 2ull);
+    const uint64_t vecs = DENSE >= 2 ? (p.tab_entries + 1) / 2 : p.tab_entries * (DENSE ? 1ull : 2ull);
     for (uint64_t i = g.lane; i < vecs; i += G) t[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
   } else if (DENSE) {
     if ((uint64_t)n * 4 < p.tab_entries) {
       for (uint32_t i = g.lane; i < n; i += G) {
         uint32_t P, SF;
         lean_keyof_load<1>(p, c, i, P, SF);
-        if (DENSE == 2) *reinterpret_cast<uint2*>(c.base + (uint64_t)lean_dense_pos(p, P, SF) * 8) = make_uint2(~0u, ~0u);
+        if (DENSE >= 2) *reinterpret_cast<uint2*>(c.base + (uint64_t)lean_dense_pos(p, P, SF) * 8) = make_uint2(~0u, ~0u);
         else *reinterpret_cast<uint4*>(c.base + (uint64_t)lean_dense_pos(p, P, SF) * 16) = make_uint4(~0u, ~0u, ~0u, ~0u);
       }
     } else {
       uint4* t = reinterpret_cast<uint4*>(c.base);
-      const uint64_t vecs = DENSE == 2 ? (p.tab_entries + 1) / 2 : p.tab_entries;   // the table is padded to 128 bytes
+      const uint64_t vecs = DENSE >= 2 ? (p.tab_entries + 1) / 2 : p.tab_entries;   // the table is padded to 128 bytes
       for (uint64_t i = g.lane; i < vecs; i += G) t[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
     }
   } else {

@@ -679,8 +679,8 @@ class Engine {
     g->slab = g->G == 8 ? fst->view.wslab != nullptr : fst->view.slab_lanes == g->G;
     g->eager = cfg.semantics == 1;
     const uint64_t E = (uint64_t)(max_len + 1) * fst->view.num_states * 2;
-    // compact 8-byte records: lean kernel, lazy semantics, integer weights, ids below 2^22 - 1
-    const bool crec = crec_ok && !wave && cfg.semantics == 0 && std::min<uint64_t>(tuple_cap, E) < kCrecNone &&
+    // compact 8-byte records: lean kernel, integer weights, ids below 2^22 - 1 (eager: 2^21 - 1, one bit is the BFS flag)
+    const bool crec = crec_ok && !wave && std::min<uint64_t>(tuple_cap, E) < (cfg.semantics == 1 ? kCrecBfsBit - 1u : kCrecNone) &&
                       std::getenv("LIBFST_B200_NO_CREC") == nullptr;
     const uint64_t rec_bytes = crec ? 8 : 16;
     const bool dense_ok = E < 0xFFFFFF00ull && E * rec_bytes <= kDenseLimitBytes;
@@ -726,7 +726,7 @@ class Engine {
 
   template <int G, bool EAGER>
   static const void* lean_kernel_ptr_ge(const Geom& g) {
-    if (!EAGER && g.crec) return g.slab ? (const void*)csp_batch_lean_kernel<G, 2, true, false> : (const void*)csp_batch_lean_kernel<G, 2, false, false>;
+    if (g.crec) return g.slab ? (const void*)csp_batch_lean_kernel<G, EAGER ? 3 : 2, true, EAGER> : (const void*)csp_batch_lean_kernel<G, EAGER ? 3 : 2, false, EAGER>;
     if (g.dense) return g.slab ? (const void*)csp_batch_lean_kernel<G, 1, true, EAGER> : (const void*)csp_batch_lean_kernel<G, 1, false, EAGER>;
     return g.slab ? (const void*)csp_batch_lean_kernel<G, 0, true, EAGER> : (const void*)csp_batch_lean_kernel<G, 0, false, EAGER>;
   }
