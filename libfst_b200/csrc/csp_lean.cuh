@@ -749,7 +749,7 @@ __device__ __forceinline__ bool lean_step(const SearchParams& p, const Group<G>&
   uint4 sa = make_uint4(0xFFFFFFFFu, 0x80000000u, 0, 0);
   uint4 rec = make_uint4(0, 0, 0, 0);
   uint32_t x = 0xFFFFFFFDu;
-  bool big = false;
+  bool big = false, csr = false;   // csr: the lanes hold CSR search records (full ilabel, one relax call each)
   // 8 lanes per string read the LEADER slab: one record per (ilabel, nextstate) group, labels first then the
   // input-epsilon records (lane order == expansion order), x = ilabel | folded arc count << 16
   constexpr bool LEADERS = SLAB && G == 8;
@@ -758,6 +758,20 @@ __device__ __forceinline__ bool lean_step(const SearchParams& p, const Group<G>&
     if (LEADERS) {
       sa = lean_ld_keep(&F.wslab[(uint64_t)s2 * kWaveSlots + g.lane]);
       big = sa.x == kWaveBig;
+      if (big && F.bigidx) {
+        // a state wider than the slab: its label index gives the arcs with the string's label and the epsilon prefix;
+        // if those fit the group (nearly always: a trie node has one child per label) they are fetched from the CSR
+        // search records, match arcs first, and take the same single relax step as any other state
+        const uint2* bi = F.bigidx + (uint64_t)sa.z * 257u;
+        const uint2 e = __ldg(bi);
+        const uint2 m = x <= 256u ? __ldg(bi + x) : make_uint2(0u, 0u);
+        if (m.y + e.y <= (uint32_t)G) {
+          sa = make_uint4(0xFFFFFFFFu, 0x80000000u, 0, 0);
+          if (g.lane < m.y) sa = __ldg(&F.sarc[m.x + g.lane]);
+          else if (g.lane < m.y + e.y) sa = __ldg(&F.sarc[e.x + (g.lane - m.y)]);
+          big = false; csr = true;
+        }
+      }
     } else if (SLAB) {
       sa = __ldg(&F.slab[(uint64_t)s2 * G + g.lane]);
       big = sa.x == 0xFFFFFFFEu;
@@ -768,11 +782,11 @@ __device__ __forceinline__ bool lean_step(const SearchParams& p, const Group<G>&
       if (!big && g.lane < deg) sa = __ldg(&F.sarc[rec.x + g.lane]);
     }
   }
-  const uint32_t lab = LEADERS ? (sa.x & 0xFFFFu) : sa.x;
+  const uint32_t lab = (LEADERS && !csr) ? (sa.x & 0xFFFFu) : sa.x;
   const bool is_match = lab == x;                  // x is never 0xFFFFFFFF / 0xFFFFFFFE / 0xFFFF (labels are byte + 1)
   const bool is_eps = lab == 0u;                   // ilabel 0 only occurs in the epsilon records
   const unsigned first = LEADERS ? Group<G>::kBits : lean_ballot<G, HOT>(g, is_match);
-  const uint32_t my_cnt = (is_match || is_eps) ? (LEADERS ? (sa.x >> 16) : 1u) : 0u;
+  const uint32_t my_cnt = (is_match || is_eps) ? ((LEADERS && !csr) ? (sa.x >> 16) : 1u) : 0u;
   lean_relax<G, DENSE, HOT, EAGER>(p, g, c, st, cur_id, my_cnt, (is_match || is_eps) && !(sa.y >> 31), is_match ? s1 + 1u : s1,
                             (sa.y << 1) | (is_match ? 0u : 1u), __hiloint2double((int)sa.w, (int)sa.z), first, bfs, bfs_dist);
   if (live && big) {

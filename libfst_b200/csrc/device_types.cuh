@@ -41,6 +41,10 @@ struct DevFstView {
   // with more than 8 records (or a group of more than 65535 arcs) holds the marker 0xFFFFFFFE in every slot.
   // Arcs with ilabel > 256 never match a byte string and are left out.  null: not built.
   const uint4* wslab;
+  // label index of the states the leader slab cannot hold (their marker record carries the index number in z):
+  // bigidx[(n * 257 + label)] = {first arc, arc count} of the state's arcs with that ilabel (label 0 = the
+  // input-epsilon prefix), so that an expansion fetches only the few arcs that can match.  null: not built.
+  const uint2* bigidx;
 };
 
 // General (non-linear) left operand as CSR in STORED arc order

@@ -50,7 +50,8 @@ struct DeviceFst {
   DevFstView view{};
   void* block = nullptr;   // one allocation holding all arrays
   void* slab_block = nullptr;   // fixed-stride search records (lean kernel), may be null
-  void* wslab_block = nullptr;  // leader-only fixed-stride search records (wave kernel), may be null
+  void* wslab_block = nullptr;  // leader-only fixed-stride search records (lean kernel with 8 lanes, wave kernel), may be null
+  void* bigidx_block = nullptr; // label index of the states the leader slab cannot hold, may be null
   bool int_weights = false;     // every finite arc / final weight is a non-negative integer <= 4095: compact 8-byte table records apply
   bool wave_ok = false;         // wave slab built and at least 90 % of the states fit it
   size_t bytes = 0;
@@ -160,7 +161,7 @@ inline cudaError_t upload_fst(const HostFrozen& f, int device, DeviceFst** out) 
       cudaGetLastError(); cudaFree(d->slab_block); d->slab_block = nullptr;
     }
   }
-  d->view.wslab = nullptr;
+  d->view.wslab = nullptr; d->view.bigidx = nullptr;
   if (lean_ok && (uint64_t)S * kWaveSlots * 16 <= (256ull << 20)) {
     std::vector<uint4> ws((size_t)S * kWaveSlots, make_uint4(0xFFFFFFFFu, 0u, 0u, 0u));
     uint32_t n_big = 0;
@@ -196,6 +197,30 @@ inline cudaError_t upload_fst(const HostFrozen& f, int device, DeviceFst** out) 
     } else {
       cudaGetLastError(); cudaFree(d->wslab_block); d->wslab_block = nullptr;
     }
+    // label index for the states that do not fit the slab (trie roots, the 256-way identity state of a tagger ...)
+    if (d->view.wslab && n_big > 0 && (uint64_t)n_big * 257 * 8 <= (64ull << 20)) {
+      std::vector<uint2> bi((size_t)n_big * 257, make_uint2(0u, 0u));
+      uint32_t nb = 0;
+      for (uint32_t s = 0; s < S; s++) {
+        if (ws[(size_t)s * kWaveSlots].x != kWaveBig) continue;
+        const uint32_t b = st[s].arc_offset, e = b + st[s].num_arcs;
+        for (uint32_t a = b; a < e;) {
+          uint32_t a2 = a;
+          while (a2 < e && ar[a2].ilabel == ar[a].ilabel) a2++;
+          if (ar[a].ilabel <= 256u) bi[(size_t)nb * 257 + ar[a].ilabel] = make_uint2(a, a2 - a);
+          a = a2;
+        }
+        for (uint32_t k = 0; k < kWaveSlots; k++) ws[(size_t)s * kWaveSlots + k].z = nb;
+        nb++;
+      }
+      if (cudaMalloc(&d->bigidx_block, bi.size() * 8) == cudaSuccess &&
+          cudaMemcpy(d->bigidx_block, bi.data(), bi.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
+          cudaMemcpy(d->wslab_block, ws.data(), ws.size() * 16, cudaMemcpyHostToDevice) == cudaSuccess) {
+        d->view.bigidx = static_cast<const uint2*>(d->bigidx_block);
+      } else {
+        cudaGetLastError(); cudaFree(d->bigidx_block); d->bigidx_block = nullptr;
+      }
+    }
   }
   *out = d;
   return cudaSuccess;
@@ -207,6 +232,7 @@ inline void free_device_fst(DeviceFst* d) {
   cudaFree(d->block);
   cudaFree(d->slab_block);
   cudaFree(d->wslab_block);
+  cudaFree(d->bigidx_block);
   if (cur != d->device) cudaSetDevice(cur);
   delete d;
 }
@@ -674,7 +700,7 @@ class Engine {
       return true;
     }
     g->kind = kLean;
-    g->G = (cfg.lanes_per_string == 8 || cfg.lanes_per_string == 16 || cfg.lanes_per_string == 32) ? cfg.lanes_per_string : fst->lean_lanes;
+    g->G = (cfg.lanes_per_string == 4 || cfg.lanes_per_string == 8 || cfg.lanes_per_string == 16 || cfg.lanes_per_string == 32) ? cfg.lanes_per_string : fst->lean_lanes;
     if (wave) { g->kind = kWave; g->G = 32; }
     g->slab = g->G == 8 ? fst->view.wslab != nullptr : fst->view.slab_lanes == g->G;
     g->eager = cfg.semantics == 1;
@@ -694,7 +720,7 @@ class Engine {
     if (g->kind == kWave) {
       // the arbitration key is the compact 32-bit tuple key (position << key_sbits | state << 1 | filter)
       uint32_t sb = 1; while ((1ull << sb) < (uint64_t)fst->view.num_states * 2) sb++;
-      if (((uint64_t)(max_len + 1) << sb) > 0xFFFFFFF0ull) { g->kind = kLean; g->G = (cfg.lanes_per_string == 8 || cfg.lanes_per_string == 16 || cfg.lanes_per_string == 32) ? cfg.lanes_per_string : fst->lean_lanes; g->slab = g->G == 8 ? fst->view.wslab != nullptr : fst->view.slab_lanes == g->G; }
+      if (((uint64_t)(max_len + 1) << sb) > 0xFFFFFFF0ull) { g->kind = kLean; g->G = (cfg.lanes_per_string == 4 || cfg.lanes_per_string == 8 || cfg.lanes_per_string == 16 || cfg.lanes_per_string == 32) ? cfg.lanes_per_string : fst->lean_lanes; g->slab = g->G == 8 ? fst->view.wslab != nullptr : fst->view.slab_lanes == g->G; }
     }
     if (g->dense) {
       if ((uint64_t)tuple_cap > E) tuple_cap = (uint32_t)E;
@@ -733,7 +759,7 @@ class Engine {
   template <int G>
   static const void* lean_kernel_ptr_g(const Geom& g) { return g.eager ? lean_kernel_ptr_ge<G, true>(g) : lean_kernel_ptr_ge<G, false>(g); }
   static const void* lean_kernel_ptr(const Geom& g) {
-    return g.G == 8 ? lean_kernel_ptr_g<8>(g) : (g.G == 16 ? lean_kernel_ptr_g<16>(g) : lean_kernel_ptr_g<32>(g));
+    return g.G == 4 ? lean_kernel_ptr_g<4>(g) : (g.G == 8 ? lean_kernel_ptr_g<8>(g) : (g.G == 16 ? lean_kernel_ptr_g<16>(g) : lean_kernel_ptr_g<32>(g)));
   }
   static const void* kernel_ptr(const Geom& g) {
     if (g.kind == kWarp) return (const void*)csp_batch_warp_kernel;

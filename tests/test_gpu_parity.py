@@ -255,7 +255,7 @@ def test_cycle_hazard_is_reported(L, O, gpu):
     assert L.compose_frozen_shortest_path(L.MutableFst.compile_string(s), fprod, 1) is None   # reference: OOM -> invalid handle
 
 
-@pytest.mark.parametrize("engine,lanes", [(1, 0), (2, 32), (2, 16), (2, 8), (3, 32), (3, 16), (3, 8), (0, 0), (4, 0), (5, 0), (6, 0), (7, 0)])
+@pytest.mark.parametrize("engine,lanes", [(1, 0), (2, 32), (2, 16), (2, 8), (3, 32), (3, 16), (3, 8), (0, 0), (4, 0), (5, 0), (6, 0), (7, 0), (2, 4), (3, 4)])
 def test_engines_agree(L, O, gpu, engine, lanes):
     """Every kernel choice for byte-string batches (general warp kernel, lean + hash table, lean + dense table;
     32 or 16 lanes per string) must reproduce the oracle bit for bit, in early-exit and exhaustive mode."""
@@ -305,7 +305,7 @@ def test_lean_window_eviction_and_levels(L, O, gpu):
     fprod, forc, _ = frozen_pair(L, O, Spec(n, 0, [0.0 if rng.random() < 0.3 else None for _ in range(n)], arcs))
     strings = [bytes(rng.randint(0, 1) for _ in range(rng.randint(20, 60))) for _ in range(24)]
     try:
-        for engine, lanes in ((2, 32), (3, 32), (3, 16), (2, 16), (3, 8), (2, 8), (0, 0), (5, 0), (6, 0)):
+        for engine, lanes in ((2, 32), (3, 32), (3, 16), (2, 16), (3, 8), (2, 8), (0, 0), (5, 0), (6, 0), (3, 4), (2, 4)):
             for exhaustive in (1, 0):
                 L.configure(engine=engine, lanes_per_string=lanes, exhaustive=exhaustive)
                 res = assert_batch_matches_oracle(L, O, fprod, forc, strings)
@@ -332,7 +332,7 @@ def test_wetext_style_config4(L, O, gpu):
         os.unlink(path)
     strings = synth.wetext_strings(sources, 160, seed=3, lo=0, hi=80)
     try:
-        for engine, lanes in ((0, 0), (2, 8), (2, 16), (2, 32), (1, 0)):
+        for engine, lanes in ((0, 0), (2, 4), (2, 8), (2, 16), (2, 32), (1, 0)):
             L.configure(engine=engine, lanes_per_string=lanes)
             res = assert_batch_matches_oracle(L, O, fprod, forc, strings)
             assert (res.status == L.PATH).all()
@@ -342,7 +342,7 @@ def test_wetext_style_config4(L, O, gpu):
         L.configure()
 
 
-@pytest.mark.parametrize("engine,lanes", [(0, 0), (2, 32), (3, 16), (2, 8), (3, 8)])
+@pytest.mark.parametrize("engine,lanes", [(0, 0), (2, 32), (3, 16), (2, 8), (3, 8), (3, 4)])
 def test_eager_semantics_config5(L, O, gpu, engine, lanes):
     """BASELINE config 5 / SURVEY rows a14+a15: the path of compose() followed by shortestPath() (different
     tie-breaking than the lazy search: lattice states numbered in FIFO order, no label tie-break)."""
