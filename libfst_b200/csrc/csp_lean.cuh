@@ -410,10 +410,18 @@ __device__ __forceinline__ void lean_chunk_free(const SearchParams& p, const Gro
   if (g.lane == 0) { LEAN_CHUNKS(p, c)[(uint64_t)ch * 32] = fh; cold[kcFreeHead] = ch; }
   g.sync();
 }
-// Append ids to radix buckets (collective).  `b` in 1..64 for active lanes.
+// Radix-heap chunk (128 bytes): word 0 = next chunk, words 1..10 = ids, words 12..31 = the distance keys the ids were
+// pushed with (8 bytes each).  Keeping the key beside the id lets a level advance classify the entries of a bucket
+// without a table lookup per entry; an entry is checked against the tuple's current distance only when it is about
+// to enter the ready set (a stale entry — the tuple was lowered again later — is dropped there).
+constexpr uint32_t kLeanChunkIds = 10;
+__device__ __forceinline__ unsigned long long* lean_chunk_keys(uint32_t* chunks, uint32_t ch) {
+  return reinterpret_cast<unsigned long long*>(chunks + (uint64_t)ch * 32 + 12);
+}
+// Append (id, key) entries to radix buckets (collective).  `b` in 1..64 for active lanes.
 template <int G>
 __device__ __forceinline__ void lean_bucket_push(const SearchParams& p, const Group<G>& g, const LeanCtx& c, LeanState& st, bool active,
-                                                 uint32_t id, uint32_t b) {
+                                                 uint32_t id, uint32_t b, unsigned long long key) {
   unsigned m = g.ballot(active);
   const unsigned lt = g.lt_mask();
   uint32_t* chunks = LEAN_CHUNKS(p, c);
@@ -427,17 +435,17 @@ __device__ __forceinline__ void lean_bucket_push(const SearchParams& p, const Gr
     const uint32_t k = __popc(same), rank = __popc(same & lt);
     const bool empty = !((occ >> (bb - 1)) & 1ull);
     const uint2 hb = LEAN_BUCKET(c)[bb - 1];
-    uint32_t head = empty ? kNoChunk : hb.x, cnt = empty ? kChunkIds : hb.y;
-    const uint32_t space = kChunkIds - cnt;
-    if (mine && rank < space) chunks[(uint64_t)head * 32 + 1 + cnt + rank] = id;
+    uint32_t head = empty ? kNoChunk : hb.x, cnt = empty ? kLeanChunkIds : hb.y;
+    const uint32_t space = kLeanChunkIds - cnt;
+    if (mine && rank < space) { chunks[(uint64_t)head * 32 + 1 + cnt + rank] = id; lean_chunk_keys(chunks, head)[cnt + rank] = key; }
     uint32_t left = k > space ? k - space : 0, done = k - left;
     if (left == 0) cnt += k;
     while (left > 0) {
       const uint32_t ch = lean_chunk_alloc<G>(p, g, c, st);
       if (st.heap_overflow) return;
-      const uint32_t take = left < kChunkIds ? left : kChunkIds;
+      const uint32_t take = left < kLeanChunkIds ? left : kLeanChunkIds;
       if (g.lane == 0) chunks[(uint64_t)ch * 32] = head;
-      if (mine && rank >= done && rank < done + take) chunks[(uint64_t)ch * 32 + 1 + (rank - done)] = id;
+      if (mine && rank >= done && rank < done + take) { chunks[(uint64_t)ch * 32 + 1 + (rank - done)] = id; lean_chunk_keys(chunks, ch)[rank - done] = key; }
       head = ch; cnt = take; done += take; left -= take;
     }
     g.sync();
@@ -468,7 +476,7 @@ __device__ __forceinline__ void lean_build_radix(const SearchParams& p, const Gr
       k = (unsigned long long)__double_as_longlong(lean_dist_of_id<DENSE>(p, c, j));
       valid = k > st.last;
     }
-    if (g.any(valid)) lean_bucket_push<G>(p, g, c, st, valid, j, valid ? bucket_of(k, st.last) : 1u);
+    if (g.any(valid)) lean_bucket_push<G>(p, g, c, st, valid, j, valid ? bucket_of(k, st.last) : 1u, k);
   }
 }
 
@@ -493,57 +501,43 @@ __device__ __forceinline__ bool lean_advance_level(const SearchParams& p, const 
     if (occ == 0) return false;
     const uint32_t b0 = __ffsll((long long)occ);   // bucket number 1..64
     const uint2 hb = LEAN_BUCKET(c)[b0 - 1];
-    // pass 1: smallest valid key in the bucket
+    // pass 1: smallest key in the bucket (the keys stored with the ids: no table access; a stale entry can only make
+    // the level a distance at which nothing turns out to be ready, and its key is never below a valid one's)
     unsigned long long m = ~0ull;
     {
       uint32_t ch = hb.x, cnt = hb.y;
       while (ch != kNoChunk) {
-        const uint32_t* cp = chunks + (uint64_t)ch * 32;
-        const uint32_t next = cp[0];
-        for (uint32_t o = 0; o < cnt; o += G) {
-          if (o + g.lane < cnt) {
-            const uint32_t id = cp[1 + o + g.lane];
-            const unsigned long long k = (unsigned long long)__double_as_longlong(lean_dist_of_id<DENSE>(p, c, id));
-            if (k > st.last && bucket_of(k, st.last) == b0 && k < m) m = k;
-          }
-        }
-        ch = next; cnt = kChunkIds;
+        const uint32_t next = chunks[(uint64_t)ch * 32];
+        const unsigned long long* kp = lean_chunk_keys(chunks, ch);
+        for (uint32_t o = g.lane; o < cnt; o += G) { const unsigned long long k = kp[o]; if (k < m) m = k; }
+        ch = next; cnt = kLeanChunkIds;
       }
       m = lean_group_min_u64<G>(g, m);
     }
     g.sync();
     lean_set_occupied<G>(p, g, c, occ & ~(1ull << (b0 - 1)));
     g.sync();
-    if (m == ~0ull) {   // only stale entries: recycle the chunks
-      uint32_t ch = hb.x;
-      while (ch != kNoChunk) {
-        const uint32_t next = chunks[(uint64_t)ch * 32];
-        lean_chunk_free<G>(p, g, c, ch);
-        ch = next;
-      }
-      continue;
-    }
     if (!p.exhaustive && have_best && __longlong_as_double((long long)m) > best_total) return false;
-    // pass 2: redistribute relative to the new level key m
-    const unsigned long long old_last = st.last;
+    // pass 2: entries at the new level key m enter the ready set if they are current (the tuple still has that
+    // distance); the others move to the bucket of their key relative to m
     st.last = m;
     uint32_t ch = hb.x, cnt = hb.y;
     while (ch != kNoChunk && !st.heap_overflow) {
       const uint32_t* cp = chunks + (uint64_t)ch * 32;
+      const unsigned long long* kp = lean_chunk_keys(chunks, ch);
       const uint32_t next = cp[0];
       for (uint32_t o = 0; o < cnt && !st.heap_overflow; o += G) {
-        bool valid = false; uint32_t id = 0; unsigned long long k = 0;
+        bool have = false, ready = false; uint32_t id = 0; unsigned long long k = 0;
         if (o + g.lane < cnt) {
-          id = cp[1 + o + g.lane];
-          k = (unsigned long long)__double_as_longlong(lean_dist_of_id<DENSE>(p, c, id));
-          valid = k > old_last && bucket_of(k, old_last) == b0;
+          have = true; id = cp[1 + o + g.lane]; k = kp[o + g.lane];
+          if (k == m) ready = (unsigned long long)__double_as_longlong(lean_dist_of_id<DENSE>(p, c, id)) == m;
         }
-        lean_ready_insert<G, false>(p, g, c, st, valid && k == m, id);
-        const bool tb = valid && k != m;
-        if (g.any(tb)) lean_bucket_push<G>(p, g, c, st, tb, id, tb ? bucket_of(k, m) : 1u);
+        lean_ready_insert<G, false>(p, g, c, st, ready, id);
+        const bool tb = have && k != m;
+        if (g.any(tb)) lean_bucket_push<G>(p, g, c, st, tb, id, tb ? bucket_of(k, m) : 1u, k);
       }
       lean_chunk_free<G>(p, g, c, ch);   // recycle
-      ch = next; cnt = kChunkIds;
+      ch = next; cnt = kLeanChunkIds;
     }
     return !st.heap_overflow;
   }
@@ -608,7 +602,7 @@ __device__ __forceinline__ void lean_relax(const SearchParams& p, const Group<G>
   const bool to_future = lowered && k != st.last;
   if (to_future && k < st.future_min) st.future_min = k;
   if (st.sorted && !bfs) {   // cold: only this group is in here
-    if (g.any(to_future)) lean_bucket_push<G>(p, g, c, st, to_future, my_id, to_future ? bucket_of(k, st.last) : 1u);
+    if (g.any(to_future)) lean_bucket_push<G>(p, g, c, st, to_future, my_id, to_future ? bucket_of(k, st.last) : 1u, k);
   }
 }
 
@@ -752,11 +746,11 @@ __device__ __forceinline__ bool lean_step(const SearchParams& p, const Group<G>&
   bool big = false, csr = false;   // csr: the lanes hold CSR search records (full ilabel, one relax call each)
   // 8 lanes per string read the LEADER slab: one record per (ilabel, nextstate) group, labels first then the
   // input-epsilon records (lane order == expansion order), x = ilabel | folded arc count << 16
-  constexpr bool LEADERS = SLAB && G == 8;
+  constexpr bool LEADERS = SLAB && (G == 8 || G == 4);
   if (live) {
     x = s1 < lhs.len ? (uint32_t)__ldg(lhs.s + s1) + 1u : 0xFFFFFFFDu;
     if (LEADERS) {
-      sa = lean_ld_keep(&F.wslab[(uint64_t)s2 * kWaveSlots + g.lane]);
+      sa = lean_ld_keep(G == 8 ? &F.wslab[(uint64_t)s2 * kWaveSlots + g.lane] : &F.wslab4[(uint64_t)s2 * 4 + g.lane]);
       big = sa.x == kWaveBig;
       if (big && F.bigidx) {
         // a state wider than the slab: its label index gives the arcs with the string's label and the epsilon prefix;

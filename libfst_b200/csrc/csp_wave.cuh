@@ -198,7 +198,7 @@ __device__ __forceinline__ bool wave_chunk(const SearchParams& p, const Group<32
       }
     }
     if (st.sorted && !st.heap_overflow) {
-      if (g.any(to_future)) lean_bucket_push<32>(p, g, c, st, to_future, my_id, to_future ? bucket_of(ndm, st.last) : 1u);
+      if (g.any(to_future)) lean_bucket_push<32>(p, g, c, st, to_future, my_id, to_future ? bucket_of(ndm, st.last) : 1u, ndm);
     }
   }
   st.n_tuples += total_new;

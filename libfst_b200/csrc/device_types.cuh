@@ -41,6 +41,9 @@ struct DevFstView {
   // with more than 8 records (or a group of more than 65535 arcs) holds the marker 0xFFFFFFFE in every slot.
   // Arcs with ilabel > 256 never match a byte string and are left out.  null: not built.
   const uint4* wslab;
+  // the same with 4 records per state (lean kernel with 4 lanes per string: sparse transducers — most states of a
+  // real grammar have one or two arcs); a state with more than 4 records holds the marker in every slot.  null: not built.
+  const uint4* wslab4;
   // label index of the states the leader slab cannot hold (their marker record carries the index number in z):
   // bigidx[(n * 257 + label)] = {first arc, arc count} of the state's arcs with that ilabel (label 0 = the
   // input-epsilon prefix), so that an expansion fetches only the few arcs that can match.  null: not built.

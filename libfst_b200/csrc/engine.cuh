@@ -51,6 +51,7 @@ struct DeviceFst {
   void* block = nullptr;   // one allocation holding all arrays
   void* slab_block = nullptr;   // fixed-stride search records (lean kernel), may be null
   void* wslab_block = nullptr;  // leader-only fixed-stride search records (lean kernel with 8 lanes, wave kernel), may be null
+  void* wslab4_block = nullptr; // ... 4 records per state (lean kernel with 4 lanes), built for sparse transducers only
   void* bigidx_block = nullptr; // label index of the states the leader slab cannot hold, may be null
   bool int_weights = false;     // every finite arc / final weight is a non-negative integer <= 4095: compact 8-byte table records apply
   bool wave_ok = false;         // wave slab built and at least 90 % of the states fit it
@@ -161,7 +162,7 @@ inline cudaError_t upload_fst(const HostFrozen& f, int device, DeviceFst** out) 
       cudaGetLastError(); cudaFree(d->slab_block); d->slab_block = nullptr;
     }
   }
-  d->view.wslab = nullptr; d->view.bigidx = nullptr;
+  d->view.wslab = nullptr; d->view.wslab4 = nullptr; d->view.bigidx = nullptr;
   if (lean_ok && (uint64_t)S * kWaveSlots * 16 <= (256ull << 20)) {
     std::vector<uint4> ws((size_t)S * kWaveSlots, make_uint4(0xFFFFFFFFu, 0u, 0u, 0u));
     uint32_t n_big = 0;
@@ -197,29 +198,65 @@ inline cudaError_t upload_fst(const HostFrozen& f, int device, DeviceFst** out) 
     } else {
       cudaGetLastError(); cudaFree(d->wslab_block); d->wslab_block = nullptr;
     }
-    // label index for the states that do not fit the slab (trie roots, the 256-way identity state of a tagger ...)
-    if (d->view.wslab && n_big > 0 && (uint64_t)n_big * 257 * 8 <= (64ull << 20)) {
-      std::vector<uint2> bi((size_t)n_big * 257, make_uint2(0u, 0u));
-      uint32_t nb = 0;
+    // 4-record variant for sparse transducers (at least 95 % of the states have <= 4 leader records, fewer than 2 on
+    // average): 4 lanes per string, 8 strings per warp
+    std::vector<uint4> w4;
+    bool use4 = false;
+    if (d->view.wslab) {
+      w4.assign((size_t)S * 4, make_uint4(0xFFFFFFFFu, 0u, 0u, 0u));
+      uint64_t n_big4 = 0, n_rec = 0;
       for (uint32_t s = 0; s < S; s++) {
-        if (ws[(size_t)s * kWaveSlots].x != kWaveBig) continue;
-        const uint32_t b = st[s].arc_offset, e = b + st[s].num_arcs;
-        for (uint32_t a = b; a < e;) {
-          uint32_t a2 = a;
-          while (a2 < e && ar[a2].ilabel == ar[a].ilabel) a2++;
-          if (ar[a].ilabel <= 256u) bi[(size_t)nb * 257 + ar[a].ilabel] = make_uint2(a, a2 - a);
-          a = a2;
+        const uint4* r8 = &ws[(size_t)s * kWaveSlots];
+        uint32_t k = 0;
+        while (k < kWaveSlots && r8[k].x != 0xFFFFFFFFu && r8[k].x != kWaveBig) k++;
+        if (r8[0].x == kWaveBig || k > 4) {
+          for (uint32_t j = 0; j < 4; j++) w4[(size_t)s * 4 + j] = make_uint4(kWaveBig, 0x80000000u, 0u, 0u);
+          n_big4++; n_rec += 8;
+        } else {
+          for (uint32_t j = 0; j < k; j++) w4[(size_t)s * 4 + j] = r8[j];
+          n_rec += k;
         }
-        for (uint32_t k = 0; k < kWaveSlots; k++) ws[(size_t)s * kWaveSlots + k].z = nb;
-        nb++;
       }
-      if (cudaMalloc(&d->bigidx_block, bi.size() * 8) == cudaSuccess &&
-          cudaMemcpy(d->bigidx_block, bi.data(), bi.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
-          cudaMemcpy(d->wslab_block, ws.data(), ws.size() * 16, cudaMemcpyHostToDevice) == cudaSuccess) {
-        d->view.bigidx = static_cast<const uint2*>(d->bigidx_block);
-      } else {
-        cudaGetLastError(); cudaFree(d->bigidx_block); d->bigidx_block = nullptr;
+      // measured on the WeText-style tagger: 4 lanes are SLOWER than 8 (427 k vs 465 k strings/s) — with 8 strings per
+      // warp the group-local rare paths (level advance, fetch, finish) stall seven other strings: on request only
+      use4 = n_big4 * 20 <= (uint64_t)S && n_rec < 2ull * S && std::getenv("LIBFST_B200_LANES4") != nullptr;
+    }
+    // label index for the states that do not fit their slab (trie roots, the 256-way identity state of a tagger ...);
+    // one numbering for both slabs (every state the 8-record slab cannot hold is also too wide for the 4-record one)
+    {
+      std::vector<uint32_t> big_states;
+      for (uint32_t s = 0; s < S; s++)
+        if (ws[(size_t)s * kWaveSlots].x == kWaveBig || (use4 && w4[(size_t)s * 4].x == kWaveBig)) big_states.push_back(s);
+      if (d->view.wslab && !big_states.empty() && (uint64_t)big_states.size() * 257 * 8 <= (64ull << 20)) {
+        std::vector<uint2> bi(big_states.size() * 257, make_uint2(0u, 0u));
+        for (uint32_t nb = 0; nb < big_states.size(); nb++) {
+          const uint32_t s = big_states[nb];
+          const uint32_t b = st[s].arc_offset, e = b + st[s].num_arcs;
+          for (uint32_t a = b; a < e;) {
+            uint32_t a2 = a;
+            while (a2 < e && ar[a2].ilabel == ar[a].ilabel) a2++;
+            if (ar[a].ilabel <= 256u) bi[(size_t)nb * 257 + ar[a].ilabel] = make_uint2(a, a2 - a);
+            a = a2;
+          }
+          if (ws[(size_t)s * kWaveSlots].x == kWaveBig) for (uint32_t k = 0; k < kWaveSlots; k++) ws[(size_t)s * kWaveSlots + k].z = nb;
+          if (use4) for (uint32_t k = 0; k < 4; k++) w4[(size_t)s * 4 + k].z = nb;
+        }
+        if (cudaMalloc(&d->bigidx_block, bi.size() * 8) == cudaSuccess &&
+            cudaMemcpy(d->bigidx_block, bi.data(), bi.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
+            cudaMemcpy(d->wslab_block, ws.data(), ws.size() * 16, cudaMemcpyHostToDevice) == cudaSuccess) {
+          d->view.bigidx = static_cast<const uint2*>(d->bigidx_block);
+        } else {
+          cudaGetLastError(); cudaFree(d->bigidx_block); d->bigidx_block = nullptr;
+        }
       }
+    }
+    if (use4 && d->view.bigidx &&
+        cudaMalloc(&d->wslab4_block, w4.size() * 16) == cudaSuccess &&
+        cudaMemcpy(d->wslab4_block, w4.data(), w4.size() * 16, cudaMemcpyHostToDevice) == cudaSuccess) {
+      d->view.wslab4 = static_cast<const uint4*>(d->wslab4_block);
+      d->lean_lanes = 4;
+    } else if (use4) {
+      cudaGetLastError(); cudaFree(d->wslab4_block); d->wslab4_block = nullptr;
     }
   }
   *out = d;
@@ -233,6 +270,7 @@ inline void free_device_fst(DeviceFst* d) {
   cudaFree(d->slab_block);
   cudaFree(d->wslab_block);
   cudaFree(d->bigidx_block);
+  cudaFree(d->wslab4_block);
   if (cur != d->device) cudaSetDevice(cur);
   delete d;
 }
@@ -426,7 +464,7 @@ class Engine {
       n_items = retry;
       d_order = d_order_buf_[pass & 1];
       if (heap_retry > 0) {
-        if (heap_mult >= 256) { too_large(); break; }
+        if (heap_mult >= 4096) { too_large(); break; }
         heap_mult *= 4;
         if (heap_mult > fst->hint_heap_mult) fst->hint_heap_mult = heap_mult;
       }
@@ -702,7 +740,7 @@ class Engine {
     g->kind = kLean;
     g->G = (cfg.lanes_per_string == 4 || cfg.lanes_per_string == 8 || cfg.lanes_per_string == 16 || cfg.lanes_per_string == 32) ? cfg.lanes_per_string : fst->lean_lanes;
     if (wave) { g->kind = kWave; g->G = 32; }
-    g->slab = g->G == 8 ? fst->view.wslab != nullptr : fst->view.slab_lanes == g->G;
+    g->slab = g->G == 8 ? fst->view.wslab != nullptr : (g->G == 4 ? fst->view.wslab4 != nullptr : fst->view.slab_lanes == g->G);
     g->eager = cfg.semantics == 1;
     const uint64_t E = (uint64_t)(max_len + 1) * fst->view.num_states * 2;
     // compact 8-byte records: lean kernel, integer weights, ids below 2^22 - 1 (eager: 2^21 - 1, one bit is the BFS flag)
@@ -720,7 +758,7 @@ class Engine {
     if (g->kind == kWave) {
       // the arbitration key is the compact 32-bit tuple key (position << key_sbits | state << 1 | filter)
       uint32_t sb = 1; while ((1ull << sb) < (uint64_t)fst->view.num_states * 2) sb++;
-      if (((uint64_t)(max_len + 1) << sb) > 0xFFFFFFF0ull) { g->kind = kLean; g->G = (cfg.lanes_per_string == 4 || cfg.lanes_per_string == 8 || cfg.lanes_per_string == 16 || cfg.lanes_per_string == 32) ? cfg.lanes_per_string : fst->lean_lanes; g->slab = g->G == 8 ? fst->view.wslab != nullptr : fst->view.slab_lanes == g->G; }
+      if (((uint64_t)(max_len + 1) << sb) > 0xFFFFFFF0ull) { g->kind = kLean; g->G = (cfg.lanes_per_string == 4 || cfg.lanes_per_string == 8 || cfg.lanes_per_string == 16 || cfg.lanes_per_string == 32) ? cfg.lanes_per_string : fst->lean_lanes; g->slab = g->G == 8 ? fst->view.wslab != nullptr : (g->G == 4 ? fst->view.wslab4 != nullptr : fst->view.slab_lanes == g->G); }
     }
     if (g->dense) {
       if ((uint64_t)tuple_cap > E) tuple_cap = (uint32_t)E;
@@ -733,7 +771,7 @@ class Engine {
     if (tuple_cap > kMaxFastTuples) return false;
     g->tuple_cap = tuple_cap;
     // radix-heap pool (128-byte chunks of 31 ids): shallow until a search really needs distance levels
-    g->heap_cap = 96 + (tuple_cap / 384) * heap_mult;
+    g->heap_cap = 96 + (tuple_cap / 1024) * heap_mult;   // 10 entries per chunk; deeper only once a search has needed it
     g->bag_cap = 0;
     LeanLayout L = lean_layout((int)g->G, g->dense, g->tab_entries, g->tuple_cap, g->heap_cap, g->crec);
     g->stride = L.total; g->smem_per_group = (L.smem_words + (g->kind == kWave ? kWaveArbWords : 0u)) * 4;
