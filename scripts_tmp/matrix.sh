@@ -8,7 +8,7 @@ run --workload epsilon_dense --mixed
 run --workload ambiguous --mixed
 run --workload plain --len 96
 run --workload wetext
-run --workload ambiguous --len 251 --semantics eager --batch 4096
+run --workload ambiguous --len 251 --semantics eager
 python - <<'PY'
 import json
 for l in open('gpurun_out/matrix.jsonl'):
