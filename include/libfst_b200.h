@@ -161,6 +161,33 @@ FstError fst_compose_frozen_shortest_path_pipeline(FstHandle first, FstHandle se
                                                    const uint64_t* offsets, uint32_t n_strings,
                                                    FstB200BatchResult** out);
 
+/* Eager lattices on the device: for every string i the result of
+ * fst_compile_string(bytes_i) -> fst_compose_frozen(., b) of the reference (include/fst.h compose_frozen,
+ * src/c-api.zig:675-742, src/ops/compose.zig:29-198) as CSR: states numbered in the reference's BFS discovery
+ * order (state 0 = start), arcs of a state in the reference's order (match arcs in frozen order, then the
+ * transducer's input-epsilon arcs with ilabel 0), final weight One (x) fw2 on final states.  Finite non-negative
+ * arc weights only (FST_INVALID_ARG otherwise).  Arrays live in host memory until fst_b200_lattice_free. */
+typedef struct {
+  uint32_t n_strings;
+  const int32_t* status;          /* [n] FST_B200_PATH = lattice built (it may still have no final state),
+                                         FST_B200_NO_PATH = empty lattice (transducer without start state),
+                                         FST_B200_TOO_LARGE / FST_B200_INTERNAL                           */
+  const uint64_t* state_offsets;  /* [n+1] states of string i are [state_offsets[i], state_offsets[i+1])  */
+  const uint64_t* arc_offsets;    /* [n+1] arcs of string i are [arc_offsets[i], arc_offsets[i+1])        */
+  const uint32_t* arc_begin;      /* per state: first arc, relative to the string's arc offset; the state's
+                                     arcs end where the next state's begin (or at the string's arc count)  */
+  const double* final_weights;    /* per state (+inf = not final)                                         */
+  const uint32_t* ilabels;        /* per arc                                                              */
+  const uint32_t* olabels;
+  const double* weights;
+  const uint32_t* nextstates;     /* per arc: state number within the same string's lattice               */
+  double device_ms;
+  uint32_t launches;
+} FstB200LatticeResult;
+FstError fst_b200_compose_frozen_lattice_batch(FstHandle b, const uint8_t* bytes, const uint64_t* offsets,
+                                               uint32_t n_strings, FstB200LatticeResult** out);
+void fst_b200_lattice_free(FstB200LatticeResult* r);
+
 /* Device-resident batch (inputs already in HBM; used for kernel-level timing and
  * for callers that keep a pipeline on the GPU).  All pointers are DEVICE pointers
  * on the current device; the call is asynchronous on `stream` (a cudaStream_t)

@@ -27,6 +27,13 @@ class FstArc(C.Structure):
     _fields_ = [("ilabel", C.c_uint32), ("olabel", C.c_uint32), ("weight", C.c_double), ("nextstate", C.c_uint32)]
 
 
+class _LatticeResult(C.Structure):
+    _fields_ = [("n_strings", C.c_uint32), ("status", C.POINTER(C.c_int32)), ("state_offsets", C.POINTER(C.c_uint64)),
+                ("arc_offsets", C.POINTER(C.c_uint64)), ("arc_begin", C.POINTER(C.c_uint32)), ("final_weights", C.POINTER(C.c_double)),
+                ("ilabels", C.POINTER(C.c_uint32)), ("olabels", C.POINTER(C.c_uint32)), ("weights", C.POINTER(C.c_double)),
+                ("nextstates", C.POINTER(C.c_uint32)), ("device_ms", C.c_double), ("launches", C.c_uint32)]
+
+
 class _BatchResult(C.Structure):
     _fields_ = [("n_strings", C.c_uint32), ("status", C.POINTER(C.c_int32)), ("path_offsets", C.POINTER(C.c_uint64)),
                 ("ilabels", C.POINTER(C.c_uint32)), ("olabels", C.POINTER(C.c_uint32)), ("weights", C.POINTER(C.c_double)),
@@ -80,6 +87,9 @@ EXPORTS = {
     "fst_compose_frozen_shortest_path_batch": (C.c_int, [C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32,
                                                          C.POINTER(C.POINTER(_BatchResult))]),
     "fst_b200_batch_free": (None, [C.POINTER(_BatchResult)]),
+    "fst_b200_compose_frozen_lattice_batch": (C.c_int, [C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32,
+                                                        C.POINTER(C.POINTER(_LatticeResult))]),
+    "fst_b200_lattice_free": (None, [C.POINTER(_LatticeResult)]),
     "fst_b200_batch_device": (C.c_int, [C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
                                         C.POINTER(DeviceOut), C.c_void_p]),
     "fst_b200_mutable_add_states": (C.c_int, [C.c_uint64, C.c_uint32]),
@@ -348,6 +358,44 @@ def compose_frozen_shortest_path_batch(b: Fst, data: np.ndarray, offsets: np.nda
                            ooff, arr(r.out_bytes, ototal, np.uint8), r.device_ms, r.total_tuples, r.total_relax, r.launches, r.passes)
     finally:
         lib().fst_b200_batch_free(out)
+
+
+class LatticeBatch:
+    """Eager lattices of a batch (fst_b200_compose_frozen_lattice_batch), copied out of the library's buffers."""
+
+    def __init__(self, status, state_offsets, arc_offsets, arc_begin, finals, il, ol, w, nxt, device_ms):
+        self.status, self.state_offsets, self.arc_offsets = status, state_offsets, arc_offsets
+        self.arc_begin, self.finals, self.ilabels, self.olabels, self.weights, self.nextstates = arc_begin, finals, il, ol, w, nxt
+        self.device_ms = device_ms
+
+    def lattice(self, i):
+        """(arc_begin[n_states + 1] relative, finals, ilabels, olabels, weights, nextstates) of string i."""
+        s0, s1 = int(self.state_offsets[i]), int(self.state_offsets[i + 1])
+        a0, a1 = int(self.arc_offsets[i]), int(self.arc_offsets[i + 1])
+        ab = np.concatenate([self.arc_begin[s0:s1].astype(np.uint64), np.array([a1 - a0], np.uint64)])
+        return ab, self.finals[s0:s1], self.ilabels[a0:a1], self.olabels[a0:a1], self.weights[a0:a1], self.nextstates[a0:a1]
+
+
+def compose_frozen_lattice_batch(b: Fst, data: np.ndarray, offsets: np.ndarray) -> LatticeBatch:
+    data = np.ascontiguousarray(data, np.uint8)
+    offsets = np.ascontiguousarray(offsets, np.uint64)
+    n = len(offsets) - 1
+    keep = data if data.size else np.zeros(1, np.uint8)
+    out = C.POINTER(_LatticeResult)()
+    rc = lib().fst_b200_compose_frozen_lattice_batch(b.h, keep.ctypes.data, offsets.ctypes.data, n, C.byref(out))
+    if rc != FST_OK:
+        raise RuntimeError(f"fst_b200_compose_frozen_lattice_batch failed: FstError {rc}")
+    r = out.contents
+    try:
+        def arr(ptr, cnt, dt):
+            return np.ctypeslib.as_array(ptr, shape=(cnt,)).astype(dt, copy=True) if cnt else np.zeros(0, dt)
+        so, ao = arr(r.state_offsets, n + 1, np.uint64), arr(r.arc_offsets, n + 1, np.uint64)
+        S, A = int(so[-1]), int(ao[-1])
+        return LatticeBatch(arr(r.status, n, np.int32), so, ao, arr(r.arc_begin, S, np.uint32), arr(r.final_weights, S, np.float64),
+                            arr(r.ilabels, A, np.uint32), arr(r.olabels, A, np.uint32), arr(r.weights, A, np.float64),
+                            arr(r.nextstates, A, np.uint32), r.device_ms)
+    finally:
+        lib().fst_b200_lattice_free(out)
 
 
 def teardown():

@@ -617,6 +617,121 @@ FstError fst_compose_frozen_shortest_path_pipeline(FstHandle first, FstHandle se
   return host_batch(first, second, bytes, offsets, n_strings, out);
 }
 
+// ── eager lattices ──
+struct LatticeResultImpl {
+  FstB200LatticeResult pub;
+  std::vector<int32_t> status; std::vector<uint64_t> state_off, arc_off; std::vector<uint32_t> arc_begin, il, ol, next;
+  std::vector<double> fin, w;
+};
+
+FstError fst_b200_compose_frozen_lattice_batch(FstHandle b, const uint8_t* bytes, const uint64_t* offsets,
+                                               uint32_t n_strings, FstB200LatticeResult** out) {
+  if (!out) return FST_INVALID_ARG;
+  *out = nullptr;
+  if (!offsets || (!bytes && n_strings && offsets[n_strings] > 0)) return FST_INVALID_ARG;
+  for (uint32_t i = 0; i < n_strings; i++) if (offsets[i + 1] < offsets[i]) return FST_INVALID_ARG;
+  FrozenEntry* fb;
+  { std::lock_guard<std::mutex> lk(g_mu); fb = g_frozen.pin(b); }
+  if (!fb) return FST_INVALID_ARG;
+  PinGuard pg{b};
+  if (fb->host->has_nan) return FST_INVALID_ARG;
+  if (!device_available()) {
+    std::fprintf(stderr, "[libfst_b200] no CUDA device: the lattice builder has no CPU fallback\n");
+    return FST_INVALID_STATE;
+  }
+  cudaError_t err;
+  Engine* en = Engine::for_current_device(&err);
+  if (!en) return FST_INVALID_STATE;
+  DeviceFst* img = fb->image_for(en->device, &err);
+  if (!img) return err == cudaErrorMemoryAllocation ? FST_OOM : FST_INVALID_STATE;
+  if (!img->lean_ok) return FST_INVALID_ARG;   // the eager kernels need finite non-negative weights
+  const uint32_t n = n_strings;
+  const uint64_t nbytes = n ? offsets[n] - offsets[0] : 0;
+  uint64_t max_len = 0;
+  for (uint32_t i = 0; i < n; i++) max_len = std::max<uint64_t>(max_len, offsets[i + 1] - offsets[i]);
+  if (max_len >= (1u << 30)) return FST_INVALID_ARG;
+  std::vector<uint64_t> rel(n + 1);
+  for (uint32_t i = 0; i <= n; i++) rel[i] = offsets[i] - offsets[0];
+
+  std::lock_guard<std::mutex> lk(en->mu);
+  cudaStream_t stream = 0;
+  struct DevBuf { void* p = nullptr; ~DevBuf() { cudaFree(p); } };
+  DevBuf b_sb, b_ab, b_ns, b_na, b_begin, b_fin, b_il, b_ol, b_nx, b_w;
+  auto alloc = [](DevBuf& d, size_t bytes) { cudaFree(d.p); d.p = nullptr; return cudaMalloc(&d.p, std::max<size_t>(bytes, 16)) == cudaSuccess; };
+  if (!alloc(b_sb, (size_t)n * 8) || !alloc(b_ab, (size_t)n * 8) || !alloc(b_ns, (size_t)n * 4) || !alloc(b_na, (size_t)n * 8)) return FST_OOM;
+  LatticeOut lat;
+  lat.state_cap = (nbytes + n) * 8 + 1024; lat.arc_cap = lat.state_cap * 4;
+  BatchCounters bc;
+  uint64_t path_cap = 2 * nbytes + 16ull * n + 1024;
+  for (int attempt = 0;; attempt++) {
+    if (!alloc(b_begin, lat.state_cap * 4) || !alloc(b_fin, lat.state_cap * 8) || !alloc(b_il, lat.arc_cap * 4) || !alloc(b_ol, lat.arc_cap * 4) ||
+        !alloc(b_nx, lat.arc_cap * 4) || !alloc(b_w, lat.arc_cap * 8)) { cudaGetLastError(); return FST_OOM; }
+    lat.d_state_base = static_cast<uint64_t*>(b_sb.p); lat.d_arc_base = static_cast<uint64_t*>(b_ab.p);
+    lat.d_n_states = static_cast<uint32_t*>(b_ns.p); lat.d_n_arcs = static_cast<uint64_t*>(b_na.p);
+    lat.d_arc_begin = static_cast<uint32_t*>(b_begin.p); lat.d_final = static_cast<double*>(b_fin.p);
+    lat.d_il = static_cast<uint32_t*>(b_il.p); lat.d_ol = static_cast<uint32_t*>(b_ol.p); lat.d_next = static_cast<uint32_t*>(b_nx.p);
+    lat.d_w = static_cast<double*>(b_w.p);
+    if (en->ensure_io(n, nbytes, path_cap) != cudaSuccess) { cudaGetLastError(); return FST_OOM; }
+    const Engine::IoBuffers& io = en->io();
+    if (nbytes) cudaMemcpyAsync(io.bytes, bytes + offsets[0], nbytes, cudaMemcpyHostToDevice, stream);
+    cudaMemcpyAsync(io.offsets, rel.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, stream);
+    err = en->run_batch(img, io.bytes, io.offsets, n, (uint32_t)max_len, io.status, io.path_offsets, io.il, io.ol, io.w, io.final_w, io.n_tuples,
+                        path_cap, nullptr, nullptr, 0, stream, &bc, nullptr, &lat);
+    if (err != cudaSuccess) return err == cudaErrorMemoryAllocation ? FST_OOM : FST_INVALID_STATE;
+    const uint64_t need = std::max<uint64_t>(bc.path_required, bc.path_total);
+    bool again = false;
+    if (need > path_cap) { path_cap = need + need / 4 + 1024; again = true; }
+    if (lat.states_required > lat.state_cap) { lat.state_cap = lat.states_required + lat.states_required / 8 + 1024; again = true; }
+    if (lat.arcs_required > lat.arc_cap) { lat.arc_cap = lat.arcs_required + lat.arcs_required / 8 + 1024; again = true; }
+    if (!again) break;
+    if (attempt >= 3) return FST_OOM;
+  }
+  t_last = bc;
+  // bring everything back and put the strings in input order (the device places them in completion order)
+  auto* r = new (std::nothrow) LatticeResultImpl();
+  if (!r) return FST_OOM;
+  std::vector<uint64_t> sb(n), ab(n), na(n); std::vector<uint32_t> ns(n);
+  r->status.resize(n);
+  const Engine::IoBuffers& io = en->io();
+  if (n) {
+    cudaMemcpy(sb.data(), lat.d_state_base, (size_t)n * 8, cudaMemcpyDeviceToHost); cudaMemcpy(ab.data(), lat.d_arc_base, (size_t)n * 8, cudaMemcpyDeviceToHost);
+    cudaMemcpy(ns.data(), lat.d_n_states, (size_t)n * 4, cudaMemcpyDeviceToHost); cudaMemcpy(na.data(), lat.d_n_arcs, (size_t)n * 8, cudaMemcpyDeviceToHost);
+    cudaMemcpy(r->status.data(), io.status, (size_t)n * 4, cudaMemcpyDeviceToHost);
+  }
+  const uint64_t S = lat.states_required, A = lat.arcs_required;
+  std::vector<uint32_t> h_begin(S), h_il(A), h_ol(A), h_nx(A); std::vector<double> h_fin(S), h_w(A);
+  if (S) { cudaMemcpy(h_begin.data(), lat.d_arc_begin, S * 4, cudaMemcpyDeviceToHost); cudaMemcpy(h_fin.data(), lat.d_final, S * 8, cudaMemcpyDeviceToHost); }
+  if (A) { cudaMemcpy(h_il.data(), lat.d_il, A * 4, cudaMemcpyDeviceToHost); cudaMemcpy(h_ol.data(), lat.d_ol, A * 4, cudaMemcpyDeviceToHost);
+           cudaMemcpy(h_nx.data(), lat.d_next, A * 4, cudaMemcpyDeviceToHost); cudaMemcpy(h_w.data(), lat.d_w, A * 8, cudaMemcpyDeviceToHost); }
+  if (cudaDeviceSynchronize() != cudaSuccess) { delete r; return FST_INVALID_STATE; }
+  r->state_off.assign(n + 1, 0); r->arc_off.assign(n + 1, 0);
+  for (uint32_t i = 0; i < n; i++) { r->state_off[i + 1] = r->state_off[i] + ns[i]; r->arc_off[i + 1] = r->arc_off[i] + na[i]; }
+  r->arc_begin.resize(S); r->fin.resize(S); r->il.resize(A); r->ol.resize(A); r->next.resize(A); r->w.resize(A);
+  for (uint32_t i = 0; i < n; i++) {
+    // the search status of the eager pair says whether a best path exists; the lattice itself exists whenever the
+    // string was processed (status PATH / NO_PATH / CYCLE): report PATH for a built lattice
+    const int32_t s = r->status[i];
+    const bool built = (s == kStPath || s == kStNoPath || s == kStCycle) && (ns[i] > 0);
+    r->status[i] = built ? FST_B200_PATH : (ns[i] == 0 && (s == kStPath || s == kStNoPath) ? FST_B200_NO_PATH : map_status(s));
+    if (!built) { r->state_off[i + 1] = r->state_off[i]; r->arc_off[i + 1] = r->arc_off[i]; continue; }
+    std::copy(h_begin.begin() + sb[i], h_begin.begin() + sb[i] + ns[i], r->arc_begin.begin() + r->state_off[i]);
+    std::copy(h_fin.begin() + sb[i], h_fin.begin() + sb[i] + ns[i], r->fin.begin() + r->state_off[i]);
+    std::copy(h_il.begin() + ab[i], h_il.begin() + ab[i] + na[i], r->il.begin() + r->arc_off[i]);
+    std::copy(h_ol.begin() + ab[i], h_ol.begin() + ab[i] + na[i], r->ol.begin() + r->arc_off[i]);
+    std::copy(h_nx.begin() + ab[i], h_nx.begin() + ab[i] + na[i], r->next.begin() + r->arc_off[i]);
+    std::copy(h_w.begin() + ab[i], h_w.begin() + ab[i] + na[i], r->w.begin() + r->arc_off[i]);
+  }
+  r->pub.n_strings = n; r->pub.status = r->status.data(); r->pub.state_offsets = r->state_off.data(); r->pub.arc_offsets = r->arc_off.data();
+  r->pub.arc_begin = r->arc_begin.data(); r->pub.final_weights = r->fin.data(); r->pub.ilabels = r->il.data(); r->pub.olabels = r->ol.data();
+  r->pub.weights = r->w.data(); r->pub.nextstates = r->next.data(); r->pub.device_ms = bc.device_ms; r->pub.launches = bc.launches;
+  *out = &r->pub;
+  return FST_OK;
+}
+
+void fst_b200_lattice_free(FstB200LatticeResult* r) {
+  if (r) delete reinterpret_cast<LatticeResultImpl*>(r);   // pub is the first member
+}
+
 void fst_b200_batch_free(FstB200BatchResult* r) {
   if (!r) return;
   auto* impl = reinterpret_cast<BatchResultImpl*>(r);   // pub is the first member

@@ -827,6 +827,76 @@ __device__ __forceinline__ void lean_bfs_begin(const SearchParams& p, const Grou
   g.sync();
 }
 
+// Eager lattice as CSR: the result of compose() (compose.zig:29-198) for this string, written after
+// the BFS phase has numbered every lattice state.  State u (BFS number) = tuple key_of[u]; its arcs in the reference's
+// order: match arcs (:95-109: ilabel of the string, olabel and weight One (x) w of the transducer arc, in frozen order),
+// then the transducer's input-epsilon arcs (:138-149: ilabel 0); final weight One (x) fw2 on states at the end of the
+// string whose transducer state is final (:69-74).  Lanes take consecutive states, a group prefix sum places the arcs.
+template <int G, int DENSE>
+__device__ __forceinline__ void lean_emit_lattice(const SearchParams& p, const Group<G>& g, const LeanCtx& c, const LeanState& st,
+                                                  const LhsBytes& lhs, uint32_t idx) {
+  const DevFstView& F = p.fst;
+  const bool ok = st.bfs_started && !(st.overflow || st.heap_overflow || st.stuck) && !(DENSE >= 2 && g.any(st.wide));
+  if (!ok) return;   // the string is retried (or failed): the pass that completes it emits
+  const uint32_t n = st.n_tuples;
+  unsigned long long total = st.relax_calls;   // per-lane partial count of the BFS phase == lattice arcs
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) total += __shfl_xor_sync(g.mask, total, o, G);
+  unsigned long long sbase = 0, abase = 0;
+  if (g.lane == 0) {
+    sbase = atomicAdd(p.lat_cursors + 0, (unsigned long long)n);
+    abase = atomicAdd(p.lat_cursors + 1, total);
+    p.lat_state_base[idx] = sbase; p.lat_arc_base[idx] = abase; p.lat_n_states[idx] = n; p.lat_n_arcs[idx] = total;
+  }
+  sbase = g.shfl(sbase, 0); abase = g.shfl(abase, 0);
+  if (sbase + n > p.lat_state_cap || abase + total > p.lat_arc_cap) return;   // sizes only: the host grows the arrays
+  unsigned long long cursor = 0;
+  for (uint32_t base = 0; base < n; base += G) {
+    const uint32_t u = base + g.lane;
+    uint32_t P = 0, SF = 0, lo = 0, hi = 0, e0 = 0, e1 = 0, x = 0;
+    if (u < n) {
+      lean_keyof_load<DENSE>(p, c, u, P, SF);
+      const uint4 rec = __ldg(&F.state_rec[SF >> 1]);
+      e0 = rec.x; e1 = rec.y;
+      if (P < lhs.len) {
+        x = (uint32_t)__ldg(lhs.s + P) + 1u;
+        uint32_t l = rec.y, h = rec.z;
+        while (l < h) { const uint32_t m = l + (h - l) / 2; if (__ldg(F.ilabel + m) < x) l = m + 1; else h = m; }
+        lo = l; h = rec.z;
+        uint32_t l2 = l;
+        while (l2 < h) { const uint32_t m = l2 + (h - l2) / 2; if (__ldg(F.ilabel + m) <= x) l2 = m + 1; else h = m; }
+        hi = l2;
+      }
+    }
+    const uint32_t deg = (hi - lo) + (e1 - e0);
+    uint32_t incl = deg;
+#pragma unroll
+    for (int o = 1; o < G; o <<= 1) { const uint32_t t = __shfl_up_sync(g.mask, incl, o, G); if ((int)g.lane >= o) incl += t; }
+    const uint32_t step_total = g.shfl(incl, G - 1);
+    if (u < n) {
+      const unsigned long long first = cursor + (incl - deg);
+      p.lat_arc_begin[sbase + u] = (uint32_t)first;
+      double fin = d_inf();
+      if (P == lhs.len) { const double fw2 = F.final_w[SF >> 1]; if (!d_isinf(fw2)) fin = 0.0 + fw2; }
+      p.lat_final[sbase + u] = fin;
+      unsigned long long w = abase + first;
+      for (uint32_t a = lo; a < hi; a++, w++) {
+        const uint4 pl = __ldg(&F.payload[a]);
+        uint32_t pos, id, prev; double d;
+        lean_lookup<DENSE>(p, c, P + 1u, pl.y << 1, pos, d, id, prev);
+        p.lat_il[w] = x; p.lat_ol[w] = pl.x; p.lat_w[w] = 0.0 + __hiloint2double((int)pl.w, (int)pl.z); p.lat_next[w] = id & ~kBfsFlag;
+      }
+      for (uint32_t a = e0; a < e1; a++, w++) {
+        const uint4 pl = __ldg(&F.payload[a]);
+        uint32_t pos, id, prev; double d;
+        lean_lookup<DENSE>(p, c, P, (pl.y << 1) | 1u, pos, d, id, prev);
+        p.lat_il[w] = 0u; p.lat_ol[w] = pl.x; p.lat_w[w] = __hiloint2double((int)pl.w, (int)pl.z); p.lat_next[w] = id & ~kBfsFlag;
+      }
+    }
+    cursor += step_total;
+  }
+}
+
 // End of a string: back-track, emit the reversed path into the pool, restore the arena invariants.
 template <int G, int DENSE>
 __device__ __forceinline__ int32_t lean_finish(const SearchParams& p, const Group<G>& g, const LeanCtx& c, const LeanState& st,
@@ -1002,6 +1072,7 @@ __global__ void __launch_bounds__(128, FSTB_LEAN_MINBLOCKS) csp_batch_lean_kerne
     }
     if (phase == kFinish) {
       uint32_t plen; uint64_t poff; double fw;
+      if (EAGER && p.lat_state_base != nullptr) lean_emit_lattice<G, DENSE>(p, g, c, st, lhs, idx);
       const int32_t status = lean_finish<G, DENSE>(p, g, c, st, lhs, &plen, &poff, &fw);
       if (g.lane == 0) {
         p.status[idx] = status; p.path_len[idx] = plen; p.pool_off[idx] = poff; p.final_w[idx] = fw; p.n_tuples[idx] = st.n_tuples;

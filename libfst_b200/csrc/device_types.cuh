@@ -118,6 +118,18 @@ struct SearchParams {
   unsigned long long* relax_counter;
   unsigned long long* tuple_counter;
   unsigned long long* wave_stats;   // optional [4]: chunk steps, tuples popped by chunks, single-pop steps, abandoned chunks
+  // optional eager lattice output (csp_lean.cuh lean_emit_lattice; lat_state_base == null: off).
+  // Every string reserves n_states / n_arcs slots of the flat arrays with the two cursors; a string that does not
+  // fit writes only its sizes (the host grows the arrays and runs again).
+  unsigned long long* lat_cursors;   // [2]: states, arcs
+  uint64_t lat_state_cap, lat_arc_cap;
+  uint64_t* lat_state_base;          // [n] first slot of the string in the per-state arrays
+  uint64_t* lat_arc_base;            // [n] first slot of the string in the per-arc arrays
+  uint32_t* lat_n_states;            // [n]
+  uint64_t* lat_n_arcs;              // [n]
+  uint32_t* lat_arc_begin;           // per state: first arc of the state, relative to the string's arc base
+  double* lat_final;                 // per state: final weight (+inf = not final)
+  uint32_t* lat_il; uint32_t* lat_ol; uint32_t* lat_next; double* lat_w;   // per arc
   // outputs (indexed by string index)
   int32_t* status;
   uint32_t* path_len;

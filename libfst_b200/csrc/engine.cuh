@@ -309,6 +309,14 @@ __global__ void max_u32_kernel(const uint32_t* in, uint32_t n, uint32_t* out) {
   if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
 }
 
+// Device buffers of the optional eager-lattice output of run_batch (see SearchParams::lat_*).
+struct LatticeOut {
+  uint64_t* d_state_base = nullptr; uint64_t* d_arc_base = nullptr; uint32_t* d_n_states = nullptr; uint64_t* d_n_arcs = nullptr;   // [n]
+  uint32_t* d_arc_begin = nullptr; double* d_final = nullptr; uint64_t state_cap = 0;                                              // per state
+  uint32_t *d_il = nullptr, *d_ol = nullptr, *d_next = nullptr; double* d_w = nullptr; uint64_t arc_cap = 0;                       // per arc
+  uint64_t states_required = 0, arcs_required = 0;   // out: totals of the batch (above the capacities: grow and run again)
+};
+
 struct BatchCounters {
   uint32_t launches = 0, passes = 0;
   unsigned long long relax = 0, tuples = 0;
@@ -355,15 +363,20 @@ class Engine {
                         int32_t* d_status, uint64_t* d_path_offsets, uint32_t* d_il, uint32_t* d_ol, double* d_w,
                         double* d_final, uint32_t* d_ntuples, uint64_t path_capacity,
                         uint64_t* d_out_offsets, uint8_t* d_out_bytes, uint64_t out_capacity,
-                        cudaStream_t stream, BatchCounters* bc, const int32_t* d_skip = nullptr) {
+                        cudaStream_t stream, BatchCounters* bc, const int32_t* d_skip = nullptr, LatticeOut* lat = nullptr) {
     *bc = BatchCounters();
     if (n == 0) {
       FSTB_CUDA(cudaMemsetAsync(d_path_offsets, 0, 8, stream));
       if (d_out_offsets) FSTB_CUDA(cudaMemsetAsync(d_out_offsets, 0, 8, stream));
       return cudaStreamSynchronize(stream);
     }
-    const Config cfg = global_config();
+    Config cfg = global_config();
+    if (lat) cfg.semantics = 1;   // the lattice is the eager pair's (compose.zig numbering)
     FSTB_CUDA(ensure_scratch(n, path_capacity));
+    if (lat) {
+      FSTB_CUDA(cudaMemsetAsync(lat->d_n_states, 0, (size_t)n * 4, stream));
+      FSTB_CUDA(cudaMemsetAsync(lat->d_n_arcs, 0, (size_t)n * 8, stream));
+    }
     // counters: [0] queue_head(u32) [1] retry_count(u32) [2..3] pool_cursor(u64) [4..5] relax [6..7] tuples [8] max_tuples
     uint32_t* d_cnt = static_cast<uint32_t*>(d_small_);
     FSTB_CUDA(cudaMemsetAsync(d_cnt, 0, 64, stream));
@@ -430,6 +443,13 @@ class Engine {
       p.relax_counter = reinterpret_cast<unsigned long long*>(d_cnt + 4);
       p.tuple_counter = reinterpret_cast<unsigned long long*>(d_cnt + 6);
       p.wave_stats = reinterpret_cast<unsigned long long*>(d_cnt + 16);   // outside the 64 bytes reset per batch: cumulative
+      if (lat) {
+        p.lat_cursors = reinterpret_cast<unsigned long long*>(d_cnt + 12);
+        p.lat_state_cap = lat->state_cap; p.lat_arc_cap = lat->arc_cap;
+        p.lat_state_base = lat->d_state_base; p.lat_arc_base = lat->d_arc_base; p.lat_n_states = lat->d_n_states; p.lat_n_arcs = lat->d_n_arcs;
+        p.lat_arc_begin = lat->d_arc_begin; p.lat_final = lat->d_final;
+        p.lat_il = lat->d_il; p.lat_ol = lat->d_ol; p.lat_next = lat->d_next; p.lat_w = lat->d_w;
+      }
       p.status = d_status; p.path_len = d_path_len_; p.pool_off = d_pool_off_; p.final_w = d_final; p.n_tuples = d_ntuples;
       p.pool = d_pool_; p.pool_cap = pool_cap_;
       launch_search(gm, blocks, threads, p, stream);
@@ -508,6 +528,7 @@ class Engine {
     std::memcpy(&bc->relax, hc + 4, 8);
     std::memcpy(&bc->tuples, hc + 6, 8);
     bc->max_tuples = hc[8];
+    if (lat) { std::memcpy(&lat->states_required, hc + 12, 8); std::memcpy(&lat->arcs_required, hc + 14, 8); }
     std::memcpy(&bc->path_total, static_cast<uint8_t*>(h_small_) + 64, 8);
     float ms = 0; cudaEventElapsedTime(&ms, ev0_, ev1_);
     bc->device_ms = ms;

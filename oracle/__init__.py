@@ -82,6 +82,10 @@ def lib():
         "orc_csp_batch_bytes": (dbl, [vp, pu8, pu64, u32, u32, u32, pu32, pu32, pd, pi32, pu32, pd, pd, pu64, pu64]),
         "orc_eager_batch_bytes": (dbl, [vp, pu8, pu64, u32, u32, u32, pu32, pu32, pd, pi32, pu32, pd, pd, pu64, pu64]),
         "orc_print_string": (C.c_int32, [vp, C.c_int, pu8, u32]),
+        "orc_compose_bytes": (vp, [vp, pu8, u32]),
+        "orc_mutable_total_arcs": (C.c_uint64, [vp]),
+        "orc_mutable_start": (u32, [vp]),
+        "orc_mutable_dump": (None, [vp, pu64, pd, pu32, pu32, pd, pu32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -164,6 +168,14 @@ class Mutable:
     def freeze(self) -> "Frozen":
         return Frozen(lib().orc_freeze(self.ptr))
 
+    def dump(self):
+        """(start, arc_begin[n+1], finals[n], ilabel, olabel, weight, nextstate) in stored order."""
+        n, a = self.num_states(), lib().orc_mutable_total_arcs(self.ptr)
+        ab, fin = np.zeros(n + 1, np.uint64), np.zeros(max(n, 1), np.float64)
+        il, ol, nx, w = np.zeros(max(a, 1), np.uint32), np.zeros(max(a, 1), np.uint32), np.zeros(max(a, 1), np.uint32), np.zeros(max(a, 1), np.float64)
+        lib().orc_mutable_dump(self.ptr, _p(ab, C.c_uint64), _p(fin, C.c_double), _p(il, C.c_uint32), _p(ol, C.c_uint32), _p(w, C.c_double), _p(nx, C.c_uint32))
+        return lib().orc_mutable_start(self.ptr), ab, fin[:n], il[:a], ol[:a], w[:a], nx[:a]
+
     def print_string(self, output_tape=False):
         buf = np.zeros(1 << 16, np.uint8)
         n = lib().orc_print_string(self.ptr, int(output_tape), _p(buf, C.c_uint8), len(buf))
@@ -229,6 +241,12 @@ def eager_mutable(lhs: Mutable, fst: Frozen, n: int = 1, cap: int = 1 << 16):
     lib().orc_eager_mutable(lhs.ptr, fst.ptr, n, cap, _p(il, C.c_uint32), _p(ol, C.c_uint32), _p(w, C.c_double),
                             C.byref(info), C.byref(ls), C.byref(la))
     return _mk_path(info, il, ol, w), ls.value, la.value
+
+
+def compose_bytes(fst: Frozen, s: bytes) -> Mutable:
+    """Eager lattice compose(compile_string(s), fst) (compose.zig:29-198)."""
+    a = np.frombuffer(s, np.uint8) if len(s) else np.zeros(1, np.uint8)
+    return Mutable(lib().orc_compose_bytes(fst.ptr, _p(a, C.c_uint8), len(s)))
 
 
 def csp_batch_bytes(fst: Frozen, data: np.ndarray, offsets: np.ndarray, n_threads: int = 1, cap: int = 0, eager: bool = False):

@@ -171,6 +171,25 @@ double orc_eager_batch_bytes(void* fst, const uint8_t* bytes, const uint64_t* of
   return batch_bytes_impl(fst, bytes, offsets, n_strings, n_threads, cap, il, ol, w, status, lens, finals, totals, sum_tuples, sum_relax, true);
 }
 
+// Eager lattice of compile_string(s) o fst (compose.zig:29-198) as a new mutable; read it with the dump calls below.
+void* orc_compose_bytes(void* fst, const uint8_t* s, uint32_t len) {
+  MutableFst m = compile_string(s, len);
+  MutableLhs l{&m};
+  return new MutableFst(compose(l, *(Fst*)fst));
+}
+uint64_t orc_mutable_total_arcs(void* m) { return ((MutableFst*)m)->total_arcs(); }
+uint32_t orc_mutable_start(void* m) { return ((MutableFst*)m)->start(); }
+// CSR dump: arc_begin[num_states + 1], finals[num_states], arcs in stored order.
+void orc_mutable_dump(void* mp, uint64_t* arc_begin, double* finals, uint32_t* il, uint32_t* ol, double* w, uint32_t* next) {
+  const MutableFst& m = *(MutableFst*)mp;
+  uint64_t k = 0;
+  for (size_t s = 0; s < m.num_states(); s++) {
+    arc_begin[s] = k; finals[s] = m.final_weight((StateId)s);
+    for (const Arc& a : m.arcs((StateId)s)) { il[k] = a.ilabel; ol[k] = a.olabel; w[k] = a.weight; next[k] = a.nextstate; k++; }
+  }
+  arc_begin[m.num_states()] = k;
+}
+
 // string.zig:64-97 over a path result expressed as label arrays is trivial; the
 // mutable variant is exposed for the fst_print_* parity tests.
 int32_t orc_print_string(void* m, int output_tape, uint8_t* buf, uint32_t buf_len) {

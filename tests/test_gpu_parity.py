@@ -528,3 +528,36 @@ def test_two_stage_pipeline(L, O, gpu):
             assert res.status[i] == L.PATH and res.output(i) == p2.output_bytes()
         else:
             assert res.status[i] == L.NO_PATH
+
+
+def test_eager_lattice_csr(L, O, gpu):
+    """the lattice of compose(compile_string(s), b) as CSR from the device == the oracle's compose()
+    (compose.zig:29-198): same state numbering (BFS discovery order), same arcs in the same order, same final weights."""
+    rng = random.Random(2718)
+    cases = []
+    for case in range(20):
+        spec = random_rhs(rng, max_states=9, real=(case % 4 == 3))
+        fprod, forc, _ = frozen_pair(L, O, spec)
+        cases.append((fprod, forc, [random_string(rng, max_len=9) for _ in range(25)]))
+    for kind, lens in ((2, [0, 1, 11, 33]), (1, [0, 5, 11]), (0, [7, 40])):
+        img = gen_image(O, kind, 4096 if kind != 1 else 512, 12)
+        strings = [bytes(i % 12 for i in range(k)) if kind == 0 else bytes(k) for k in lens]
+        cases.append((L.Fst.from_image(img), O.Frozen.from_bytes(img), strings))
+    checked = 0
+    for fprod, forc, strings in cases:
+        data, offsets = L.pack_strings(strings)
+        res = L.compose_frozen_lattice_batch(fprod, data, offsets)
+        for i, s in enumerate(strings):
+            m = O.compose_bytes(forc, s)
+            start, ab, fin, il, ol, w, nx = m.dump()
+            if m.num_states() == 0:
+                assert res.status[i] == L.NO_PATH, (i, s, res.status[i])
+                continue
+            assert res.status[i] == L.PATH and start == 0, (i, s, res.status[i])
+            gab, gfin, gil, gol, gw, gnx = res.lattice(i)
+            assert np.array_equal(gab, ab), (i, s, gab[:8], ab[:8])
+            assert np.array_equal(gfin.view(np.uint64), fin.view(np.uint64)), (i, s)
+            assert np.array_equal(gil, il) and np.array_equal(gol, ol) and np.array_equal(gnx, nx), (i, s)
+            assert np.array_equal(gw.view(np.uint64), w.view(np.uint64)), (i, s)
+            checked += 1
+    assert checked > 300
