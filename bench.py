@@ -195,7 +195,7 @@ def run_reference(args):
         "impl": "reference", "metric": "strings/sec batched compose_shortest_path", "value": v, "unit": "strings/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, sample, 0),
+        "config": dict(workload_config(args, sample, 0), cache="n/a (CPU arm)"),
         "composed_arcs_per_sec": v * R1,
         "cpu_baseline": {"value": v, "unit": "strings/s", "cores": cores, "kind": "port",
                          "sample": f"{sample} strings/step of the same workload, {cores} threads, C++ restatement of the reference "
