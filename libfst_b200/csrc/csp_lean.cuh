@@ -172,29 +172,6 @@ struct LeanState {
   uint32_t occ;                  // eager BFS phase: records in the table = search tuples + tuples first met by the BFS
 };
 
-// Cache-policy experiments (compile-time): FSTB_LEAN_HINTS & 1 = search records and id -> key loads keep their L1
-// lines (evict_last); & 2 = table record loads do not allocate in L1.
-#ifndef FSTB_LEAN_HINTS
-#define FSTB_LEAN_HINTS 0
-#endif
-__device__ __forceinline__ uint4 lean_ld_keep(const uint4* q) {
-  uint4 v;
-  if (FSTB_LEAN_HINTS & 1) asm volatile("ld.global.nc.L1::evict_last.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(q));
-  else v = __ldg(q);
-  return v;
-}
-__device__ __forceinline__ uint32_t lean_ld_keep32(const uint32_t* q) {
-  uint32_t v;
-  if (FSTB_LEAN_HINTS & 1) asm volatile("ld.global.L1::evict_last.u32 %0, [%1];" : "=r"(v) : "l"(q));
-  else v = *q;
-  return v;
-}
-__device__ __forceinline__ uint2 lean_ld_rec8(const uint8_t* q) {
-  uint2 v;
-  if (FSTB_LEAN_HINTS & 2) asm volatile("ld.global.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(q));
-  else v = *reinterpret_cast<const uint2*>(q);
-  return v;
-}
 // Tuple key of the lean path as a (P, SF) pair: P = string position, SF = (transducer state << 1) | filter
 // (filter is 0 or 1 for an epsilon-free left operand; states < 2^31 is checked at upload).
 //   hash table:  64-bit key (P << 32) | SF.
@@ -218,7 +195,7 @@ __device__ __forceinline__ void lean_keyof_store(const SearchParams& p, const Le
 template <int DENSE>
 __device__ __forceinline__ void lean_keyof_load(const SearchParams& p, const LeanCtx& c, uint32_t id, uint32_t& P, uint32_t& SF) {
   if (DENSE) {
-    const uint32_t k = lean_ld_keep32(reinterpret_cast<const uint32_t*>(LEAN_KEYOF(p, c)) + id);
+    const uint32_t k = reinterpret_cast<const uint32_t*>(LEAN_KEYOF(p, c))[id];
     P = k >> p.key_sbits; SF = k & ((1u << p.key_sbits) - 1u);
   } else {
     const unsigned long long k = reinterpret_cast<const unsigned long long*>(LEAN_KEYOF(p, c))[id];
@@ -240,7 +217,7 @@ __device__ __forceinline__ void lean_lookup(const SearchParams& p, const LeanCtx
                                             uint32_t& id, uint32_t& prev) {
   if (DENSE >= 2) {
     pos = lean_dense_pos(p, P, SF);
-    const uint2 v = lean_ld_rec8(c.base + (uint64_t)pos * 8);   // x = low word: id:10 low bits | prev:22 ; y = dist:20 | id:12 high bits
+    const uint2 v = *reinterpret_cast<const uint2*>(c.base + (uint64_t)pos * 8);   // x = low word: id:10 low bits | prev:22 ; y = dist:20 | id:12 high bits
     const uint32_t i = ((v.y & 0xFFFu) << 10) | (v.x >> 22), pr = v.x & kCrecNone;
     id = i == kCrecNone ? kNone : (DENSE == 3 ? ((i & (kCrecBfsBit - 1u)) | ((i & kCrecBfsBit) ? kBfsFlag : 0u)) : i);
     prev = pr == kCrecNone ? kNone : pr;
@@ -750,7 +727,7 @@ __device__ __forceinline__ bool lean_step(const SearchParams& p, const Group<G>&
   if (live) {
     x = s1 < lhs.len ? (uint32_t)__ldg(lhs.s + s1) + 1u : 0xFFFFFFFDu;
     if (LEADERS) {
-      sa = lean_ld_keep(G == 8 ? &F.wslab[(uint64_t)s2 * kWaveSlots + g.lane] : &F.wslab4[(uint64_t)s2 * 4 + g.lane]);
+      sa = __ldg(G == 8 ? &F.wslab[(uint64_t)s2 * kWaveSlots + g.lane] : &F.wslab4[(uint64_t)s2 * 4 + g.lane]);
       big = sa.x == kWaveBig;
       if (big && F.bigidx) {
         // a state wider than the slab: its label index gives the arcs with the string's label and the epsilon prefix;

@@ -338,7 +338,15 @@ def test_wetext_style_config4(L, O, gpu):
             assert (res.status == L.PATH).all()
         L.configure(exhaustive=1)
         assert_batch_matches_oracle(L, O, fprod, forc, strings[:40])
+        # the optional 4-record leader slab (4 lanes per string picked automatically for a sparse transducer): the
+        # device image is built when the transducer is first searched, so a fresh handle sees the switch
+        os.environ["LIBFST_B200_LANES4"] = "1"
+        f4 = m.freeze()
+        L.configure()
+        res = assert_batch_matches_oracle(L, O, f4, forc, strings)
+        assert (res.status == L.PATH).all()
     finally:
+        os.environ.pop("LIBFST_B200_LANES4", None)
         L.configure()
 
 
