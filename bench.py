@@ -246,6 +246,9 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # rank 0's stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) out of it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L.load()
     L.configure(lanes_per_string=args.lanes, exhaustive=args.exhaustive, engine=args.engine, tuples_hint=args.tuples_hint,
