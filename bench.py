@@ -203,7 +203,7 @@ def run_reference(args):
         "e2e": {"value": v, "unit": "strings/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, batch, state_bytes, resident=None):
@@ -229,8 +229,26 @@ def measured_traffic(args):
         return None
 
 
+_JSON_FD = None
+
+
+def emit(line: dict):
+    """The one JSON line of the run, on the process's ORIGINAL stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
     args = parse()
+    # stdout carries exactly one JSON line: anything native libraries print there (NCCL's version banner under
+    # NCCL_DEBUG=VERSION, ...) is sent to stderr instead
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -246,9 +264,6 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        # rank 0's stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) out of it
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L.load()
     L.configure(lanes_per_string=args.lanes, exhaustive=args.exhaustive, engine=args.engine, tuples_hint=args.tuples_hint,
@@ -427,7 +442,7 @@ def main():
         line["cpu_baseline"] = {"value": sample / secs, "unit": "strings/s", "cores": cores, "kind": "port",
                                 "sample": f"first {sample} strings of the same batch on {cores} threads ({secs:.1f} s); C++ "
                                           f"restatement of the reference (zig toolchain absent)"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
