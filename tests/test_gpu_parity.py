@@ -569,3 +569,39 @@ def test_eager_lattice_csr(L, O, gpu):
             assert np.array_equal(gw.view(np.uint64), w.view(np.uint64)), (i, s)
             checked += 1
     assert checked > 300
+
+
+def test_large_batch_longest_first_order(L, O, gpu):
+    """Batches of 4096+ strings leave the work queue longest first (device radix sort by length): results must still
+    come back in input order, bit-exact, for strings of very different lengths (including empty ones)."""
+    rng = random.Random(99)
+    spec = random_rhs(rng, max_states=7, nlab=3)
+    fprod, forc, _ = frozen_pair(L, O, spec)
+    strings = [random_string(rng, nlab=3, max_len=rng.choice([0, 1, 3, 12, 30])) for _ in range(5000)]
+    data, offsets = L.pack_strings(strings)
+    res = L.compose_frozen_shortest_path_batch(fprod, data, offsets)
+    cache = {}
+    for i, s in enumerate(strings):
+        p = cache.get(s)
+        if p is None:
+            p = cache[s] = O.csp_bytes(forc, s)
+        if p.status == O.STATUS_BACKTRACK_CYCLE:
+            assert res.status[i] == L.CYCLE
+        elif p.status == O.STATUS_EMPTY:
+            assert res.status[i] == L.NO_PATH
+        else:
+            assert res.status[i] == L.PATH, (i, s)
+            il, ol, w = res.path(i)
+            assert np.array_equal(il, p.ilabels) and np.array_equal(ol, p.olabels), (i, s)
+            assert np.array_equal(w.view(np.uint64), p.weights.view(np.uint64)), (i, s)
+            assert res.output(i) == p.output_bytes(), (i, s)
+    # the same batch through the two-stage entry (stage 2 sorts stage 1's output strings)
+    res2 = L.compose_frozen_shortest_path_pipeline(fprod, fprod, data, offsets)
+    for i in range(0, 5000, 37):
+        p1 = cache[strings[i]]
+        if p1.status != O.STATUS_OK:
+            assert res2.status[i] != L.PATH
+            continue
+        p2 = O.csp_bytes(forc, p1.output_bytes())
+        if p2.status == O.STATUS_OK:
+            assert res2.status[i] == L.PATH and res2.output(i) == p2.output_bytes(), (i, strings[i])
