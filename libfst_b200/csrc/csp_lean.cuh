@@ -210,6 +210,15 @@ __device__ __forceinline__ void lean_keyof_load(const SearchParams& p, const Lea
 __device__ __forceinline__ uint32_t lean_dense_pos(const SearchParams& p, uint32_t P, uint32_t SF) {
   return P * p.dense_stride + SF;
 }
+// Hash of a tuple key for the open-addressing table: two odd multipliers and an xorshift-multiply finisher (the slot is
+// taken from the HIGH bits).  Keys are structured (small positions, clustered state numbers).  Against the 64-bit
+// finalizer used before (a quarter of the instructions): WeText-style config 4 451 k -> 472 k strings/s, ambiguous
+// len 96 forced onto the hash table 987 k -> 966 k.
+__device__ __forceinline__ uint32_t lean_hash(uint32_t P, uint32_t SF) {
+  uint32_t h = SF * 0x9E3779B1u + P * 0x85EBCA6Bu;
+  h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 13;
+  return h;
+}
 // Find the record of key (P, SF): position and contents; id == kNone <=> not present (hash: `pos` is then
 // the empty slot that ended the probe — pass it to lean_claim before storing).
 template <int DENSE>
@@ -230,7 +239,7 @@ __device__ __forceinline__ void lean_lookup(const SearchParams& p, const LeanCtx
     const unsigned long long K = ((unsigned long long)P << 32) | SF;
     const LeanSlot* tab = reinterpret_cast<const LeanSlot*>(c.base);
     const uint32_t cap = (uint32_t)p.tab_entries;
-    uint32_t i = (uint32_t)(((unsigned long long)hash_key(K) * cap) >> 32);
+    uint32_t i = (uint32_t)(((unsigned long long)lean_hash(P, SF) * cap) >> 32);
     for (;;) {
       const unsigned long long k = tab[i].key;
       if (k == kEmptyKey) { pos = i; dist = d_inf(); id = kNone; prev = kNone; return; }
