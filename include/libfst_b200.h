@@ -219,9 +219,9 @@ FstError fst_b200_mutable_add_arcs(FstMutableHandle handle, uint64_t n, const ui
 
 /* Tuning / introspection (all optional). */
 typedef struct {
-  uint64_t workspace_bytes;   /* device budget for search state; 0 = 60% of free HBM     */
-  uint32_t lanes_per_string;  /* 32, 16, 8 (4: general kernels only); 0 = choose from the
-                                 transducer's out-degree distribution */
+  uint64_t workspace_bytes;   /* device budget for search state; 0 = 95% of free HBM     */
+  uint32_t lanes_per_string;  /* 32, 16, 8, 4; 0 = choose from the transducer's out-degree
+                                 distribution (records per state after folding parallel arcs) */
   uint32_t tuples_hint;       /* expected max tuples per string; 0 = adaptive            */
   uint32_t exhaustive;        /* 1 = never stop before the queue is empty (reference's
                                  literal behaviour); 0 = stop once no remaining tuple can
