@@ -1,5 +1,11 @@
 // Wavefront exact search: ONE WARP PER STRING, up to 32 pops per step.
 //
+// STATUS: exact (parity-tested like every other engine) but NOT used by default — measured 4x slower than the lean
+// kernel on the bench transducers (profiles/README.md): the reference's pop order keeps jumping back to tuples the
+// current expansion has just lowered, so only 1.6-2 consecutive pops are order-independent on average and most
+// chunks are cut to a single tuple.  Kept selectable (`engine = 4..6`) for transducers whose levels are wide
+// breadth-first sweeps (all-zero weights without re-lowering), where whole ready words do pop together.
+//
 // The lean kernel (csp_lean.cuh) emulates the reference's pop sequence one tuple at a time and takes all of
 // its parallelism from the batch; the per-string latency (one dependent chain window -> key -> arcs -> table
 // per pop) times the number of strings that fit HBM bounds its throughput.  This kernel keeps the same data
