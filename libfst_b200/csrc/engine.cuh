@@ -276,18 +276,23 @@ inline void free_device_fst(DeviceFst* d) {
 }
 
 // small helper kernels (plumbing)
-__global__ void collect_retry_kernel(const int32_t* status, uint32_t n, uint32_t* order, uint32_t* count, uint32_t* heap_count,
-                                     uint32_t* wide_count) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n && (status[i] == kStRetry || status[i] == kStRetryHeap || status[i] == kStRetryWide)) {
+// Strings of the pass just run (work items `items[0..n)`, null = identity) that must run again.
+__global__ void collect_retry_kernel(const int32_t* status, const uint32_t* items, uint32_t n, uint32_t* order, uint32_t* count,
+                                     uint32_t* heap_count, uint32_t* wide_count) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint32_t i = items ? items[k] : k;
+  if (status[i] == kStRetry || status[i] == kStRetryHeap || status[i] == kStRetryWide) {
     order[atomicAdd(count, 1u)] = i;
     if (status[i] == kStRetryHeap) atomicAdd(heap_count, 1u);
     if (status[i] == kStRetryWide) atomicAdd(wide_count, 1u);
   }
 }
-__global__ void mark_too_large_kernel(int32_t* status, uint32_t* path_len, uint32_t n) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n && (status[i] == kStRetry || status[i] == kStRetryHeap || status[i] == kStRetryWide)) { status[i] = kStTooLarge; path_len[i] = 0; }
+__global__ void mark_too_large_kernel(int32_t* status, uint32_t* path_len, const uint32_t* items, uint32_t n) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint32_t i = items ? items[k] : k;
+  if (status[i] == kStRetry || status[i] == kStRetryHeap || status[i] == kStRetryWide) { status[i] = kStTooLarge; path_len[i] = 0; }
 }
 __global__ void fill_retry_kernel(int32_t* status, uint32_t* path_len, uint32_t n) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -384,27 +389,63 @@ class Engine {
     fill_retry_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_status, d_path_len_, n);
     bc->launches++;
 
-    uint32_t tuple_cap = cfg.tuples_hint ? cfg.tuples_hint : (fst->hint_tuples ? fst->hint_tuples + fst->hint_tuples / 4 + 64 : 4096);
-    uint32_t n_items = n, heap_mult = fst->hint_heap_mult;
-    const uint32_t* d_order = nullptr;
+    // Work segments: the batch in longest-first order, cut where the strings get so much shorter that their search state
+    // (a dense table has (length + 1) * 2S records) is worth its own arena geometry — more strings in flight for the
+    // short ones.  One segment (the whole batch, input order) for small or uniform batches.
+    struct Seg { uint32_t begin, count, max_len; };
+    std::vector<Seg> segs{{0u, n, max_len}};
+    const uint32_t* d_sorted = nullptr;
     if (n >= 4096) {
       // strings leave the work queue longest first (search cost grows with the length): the last wave of a batch of
       // mixed lengths ends with short strings instead of a few long ones running alone
       length_keys_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_offsets, n, d_sort_keys_[0], d_sort_vals_[0]);
       size_t tmp = sort_tmp_bytes_;
       FSTB_CUDA(cub::DeviceRadixSort::SortPairs(d_sort_tmp_, tmp, d_sort_keys_[0], d_sort_keys_[1], d_sort_vals_[0], d_sort_vals_[1], (int)n, 0, 32, stream));
-      d_order = d_sort_vals_[1];
+      d_sorted = d_sort_vals_[1];
       bc->launches += 3;
+      constexpr uint32_t kMinSeg = 8192;
+      // measured on the mixed eps-dense batch (57 216 strings, lengths 11..251): 3 858 strings/s in four segments vs
+      // 4 117 in one — every segment ends with its own tail and the arenas are re-initialised per geometry; opt-in
+      if (n >= 4 * kMinSeg && max_len >= 32 && fst->lean_ok && std::getenv("LIBFST_B200_SEGMENTS") != nullptr) {
+        std::vector<uint32_t> keys(n);   // ~length, ascending == lengths descending
+        FSTB_CUDA(cudaMemcpyAsync(keys.data(), d_sort_keys_[1], (size_t)n * 4, cudaMemcpyDeviceToHost, stream));
+        FSTB_CUDA(cudaStreamSynchronize(stream));
+        const uint32_t len0 = ~keys[0];
+        if ((uint64_t)(~keys[n - 1]) * 4 <= (uint64_t)len0 * 3) {
+          segs.clear();
+          uint32_t begin = 0;
+          for (int q = 3; q >= 0 && begin < n; q--) {
+            const uint32_t thr = (uint32_t)((uint64_t)len0 * (uint32_t)q / 4);   // this class: thr < length
+            const uint32_t end = q == 0 ? n : (uint32_t)(std::upper_bound(keys.begin() + begin, keys.end(), ~(thr + 1u) ) - keys.begin());
+            if (end > begin) { segs.push_back(Seg{begin, end - begin, ~keys[begin]}); begin = end; }
+          }
+          // a class with too few strings to fill the device rides with its longer neighbour, or takes the next one along
+          for (size_t i = 0; i < segs.size();) {
+            if (segs[i].count < kMinSeg && i + 1 < segs.size()) { segs[i].count += segs[i + 1].count; segs.erase(segs.begin() + i + 1); }
+            else if (segs[i].count < kMinSeg && i > 0) { segs[i - 1].count += segs[i].count; segs.erase(segs.begin() + i); }
+            else i++;
+          }
+        }
+      }
     }
     bool crec_ok = fst->int_weights && !fst->crec_failed;   // compact table records until a distance outgrows them
+    bool abort_all = false;
+    uint32_t seg_no = 0;
+    for (const Seg& sg : segs) {
+    if (abort_all) break;
+    uint32_t tuple_cap = cfg.tuples_hint ? cfg.tuples_hint : (fst->hint_tuples ? fst->hint_tuples + fst->hint_tuples / 4 + 64 : 4096);
+    uint32_t n_items = sg.count, heap_mult = fst->hint_heap_mult;
+    const uint32_t* d_order = d_sorted ? d_sorted + sg.begin : nullptr;
+    const uint32_t seg_max_len = sg.max_len;
+    FSTB_CUDA(cudaMemsetAsync(d_cnt + 0, 0, 4, stream));   // queue head
     auto too_large = [&]() {
-      mark_too_large_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_status, d_path_len_, n);
+      mark_too_large_kernel<<<(n_items + 255) / 256, 256, 0, stream>>>(d_status, d_path_len_, d_order, n_items);
       bc->launches++;
     };
     for (uint32_t pass = 0;; pass++) {
       bc->passes++;
       Geom gm;
-      if (!geometry(cfg, fst, max_len, tuple_cap, heap_mult, &gm, crec_ok, workspace_budget(cfg))) { too_large(); break; }
+      if (!geometry(cfg, fst, seg_max_len, tuple_cap, heap_mult, &gm, crec_ok, workspace_budget(cfg))) { too_large(); break; }
       if (cfg.semantics == 1 && gm.kind != kLean) {
         std::fprintf(stderr, "[libfst_b200] eager semantics need finite non-negative weights (lean kernel)\n");
         too_large(); break;
@@ -423,7 +464,7 @@ class Engine {
       }
       FSTB_CUDA(ensure_workspace(gm, blocks * gpb, stream));
       bc->launches += init_launches_; init_launches_ = 0;
-      if (pass == 0) { bc->resident = blocks * gpb; bc->capacity = std::min(max_groups, fit >= gpb ? (fit / gpb) * gpb : fit); }
+      if (pass == 0 && seg_no == 0) { bc->resident = blocks * gpb; bc->capacity = std::min(max_groups, fit >= gpb ? (fit / gpb) * gpb : fit); }
 
       SearchParams p{};
       p.fst = fst->view;
@@ -458,7 +499,7 @@ class Engine {
       // any string that overflowed its arena (or the pool)?
       FSTB_CUDA(cudaMemsetAsync(d_cnt + 1, 0, 4, stream));
       FSTB_CUDA(cudaMemsetAsync(d_cnt + 9, 0, 8, stream));
-      collect_retry_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_status, n, d_order_buf_[pass & 1], d_cnt + 1, d_cnt + 9, d_cnt + 10);
+      collect_retry_kernel<<<(n_items + 255) / 256, 256, 0, stream>>>(d_status, d_order, n_items, d_order_buf_[pass & 1], d_cnt + 1, d_cnt + 9, d_cnt + 10);
       bc->launches++;
       FSTB_CUDA(cudaMemcpyAsync(h_small_, d_cnt, 64, cudaMemcpyDeviceToHost, stream));
       FSTB_CUDA(cudaStreamSynchronize(stream));
@@ -470,14 +511,15 @@ class Engine {
         if (gm.kind == kWave) std::fprintf(stderr, "[libfst_b200] wave stats (cumulative): chunk steps %llu, tuples popped by chunks %llu, single-pop steps %llu, abandoned chunks %llu\n", ws[0], ws[1], ws[2], ws[3]);
       }
       if (std::getenv("LIBFST_B200_DEBUG"))
-        std::fprintf(stderr, "[libfst_b200] pass %u kind %d G %u dense %d eager %d tuple_cap %u heap_cap %u items %u groups %u retry %u heap_retry %u\n",
-                     pass, gm.kind, gm.G, (int)gm.dense + (int)gm.crec, (int)gm.eager, gm.tuple_cap, gm.heap_cap, n_items, blocks * gpb, retry, heap_retry);
+        std::fprintf(stderr, "[libfst_b200] segment %u/%zu (max_len %u) pass %u kind %d G %u dense %d eager %d tuple_cap %u heap_cap %u items %u groups %u retry %u heap_retry %u\n",
+                     seg_no, segs.size(), seg_max_len, pass, gm.kind, gm.G, (int)gm.dense + (int)gm.crec, (int)gm.eager, gm.tuple_cap, gm.heap_cap, n_items, blocks * gpb, retry, heap_retry);
       unsigned long long pool_used; std::memcpy(&pool_used, hc + 2, 8);
       if (retry == 0) break;
       if (pool_used > pool_cap_) {
         // path pool too small: report the requirement; caller grows and re-runs
         bc->path_required = pool_used;
         too_large();
+        abort_all = true;
         break;
       }
       // next pass: only the overflowed strings; 8x larger arenas and/or a 4x deeper radix-heap pool
@@ -495,6 +537,12 @@ class Engine {
         tuple_cap *= 8;
       }
       FSTB_CUDA(cudaMemsetAsync(d_cnt + 0, 0, 4, stream));   // queue head
+    }
+    seg_no++;
+    }   // segments
+    if (abort_all) {   // strings of the segments that never ran still carry the initial retry status
+      mark_too_large_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_status, d_path_len_, nullptr, n);
+      bc->launches++;
     }
 
     // ordered output: offsets = exclusive scan of path lengths, then un-reverse

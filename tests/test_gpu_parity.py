@@ -605,3 +605,42 @@ def test_large_batch_longest_first_order(L, O, gpu):
         p2 = O.csp_bytes(forc, p1.output_bytes())
         if p2.status == O.STATUS_OK:
             assert res2.status[i] == L.PATH and res2.output(i) == p2.output_bytes(), (i, strings[i])
+
+
+def test_length_segments(L, O, gpu):
+    """With LIBFST_B200_SEGMENTS=1, batches of 32 768+ strings whose lengths differ by more than 4:3 are searched in length
+    segments, each with its own arena geometry (LIBFST_B200_DEBUG shows them); every string must still match the
+    oracle, in input order, with both table kinds (and without the switch)."""
+    import os
+    rng = random.Random(1234)
+    spec = random_rhs(rng, max_states=6, nlab=2)
+    fprod, forc, _ = frozen_pair(L, O, spec)
+    lens = [0, 3, 10, 20, 40]
+    strings = [bytes(rng.randint(0, 1) for _ in range(lens[i % 5])) for i in range(40000)]
+    rng.shuffle(strings)
+    data, offsets = L.pack_strings(strings)
+    cache = {}
+    try:
+        for engine, seg in ((0, "1"), (2, "1"), (0, None)):
+            if seg:
+                os.environ["LIBFST_B200_SEGMENTS"] = seg
+            else:
+                os.environ.pop("LIBFST_B200_SEGMENTS", None)
+            L.configure(engine=engine)
+            res = L.compose_frozen_shortest_path_batch(fprod, data, offsets)
+            for i, s in enumerate(strings):
+                p = cache.get(s)
+                if p is None:
+                    p = cache[s] = O.csp_bytes(forc, s)
+                if p.status == O.STATUS_BACKTRACK_CYCLE:
+                    assert res.status[i] == L.CYCLE
+                elif p.status == O.STATUS_EMPTY:
+                    assert res.status[i] == L.NO_PATH, (i, s)
+                else:
+                    assert res.status[i] == L.PATH, (i, s, res.status[i])
+                    il, ol, w = res.path(i)
+                    assert np.array_equal(il, p.ilabels) and np.array_equal(ol, p.olabels), (i, s)
+                    assert np.array_equal(w.view(np.uint64), p.weights.view(np.uint64)), (i, s)
+    finally:
+        os.environ.pop("LIBFST_B200_SEGMENTS", None)
+        L.configure()
