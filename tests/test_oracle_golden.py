@@ -123,3 +123,26 @@ def test_hazard_backtrack_cycle_is_flagged(O):
     n, finals, arcs, s = CYCLE_CASE
     f = Spec(n, 0, finals, arcs).to_oracle(O).freeze()
     assert O.csp_bytes(f, s).status == O.STATUS_BACKTRACK_CYCLE
+
+
+def test_compose_bytes_lattice_dump(O):
+    """The eager lattice dump used as the checker of fst_b200_compose_frozen_lattice_batch: compose.zig:29-198 on a
+    compiled string — states in BFS discovery order, arcs of a state in frozen order (match arcs, then the
+    transducer's input-epsilon arcs with ilabel 0), final weight fw1 (x) fw2."""
+    import numpy as np
+    from common import Spec
+    # state 0: label 10 -> 1 (two parallel arcs, olabels 100 / 101), epsilon -> 2; state 1 final 0.5; state 2: label 10 -> 1
+    rhs = Spec(3, 0, [None, 0.5, None], [(0, 10, 101, 2.0, 1), (0, 10, 100, 0.0, 1), (0, 0, 7, 1.0, 2), (2, 10, 102, 0.25, 1)])
+    f = rhs.to_oracle(O).freeze()
+    m = O.compose_bytes(f, bytes([9]))            # byte 9 = label 10
+    start, ab, fin, il, ol, w, nx = m.dump()
+    # tuples: 0 = (0, s0, f0); match arcs first -> (1, s1, f0) = 1; epsilon arc -> (0, s2, f1) = 2; from 2: match -> 1
+    assert start == 0 and m.num_states() == 3
+    assert list(ab) == [0, 3, 3, 4]
+    assert list(il) == [10, 10, 0, 10] and list(ol) == [100, 101, 7, 102]
+    assert list(w) == [0.0, 2.0, 1.0, 0.25] and list(nx) == [1, 1, 2, 1]
+    assert np.isinf(fin[0]) and fin[1] == 0.5 and np.isinf(fin[2])
+    # the empty string: one state, final only if the start state is final; epsilon arcs still expand
+    m0 = O.compose_bytes(f, b"")
+    s0, ab0, fin0, il0, ol0, w0, nx0 = m0.dump()
+    assert m0.num_states() == 2 and list(il0) == [0] and list(ol0) == [7] and list(nx0) == [1] and np.isinf(fin0).all()
