@@ -220,6 +220,12 @@ def workload_config(args, batch, state_bytes, resident=None):
             "lanes_per_string": args.lanes or "auto", "exhaustive": args.exhaustive, "engine": args.engine or "auto"}
 
 
+def transducer_size(fst):
+    """States and arcs of the frozen transducer, read back through the C ABI (fst_num_states / fst_num_arcs)."""
+    n = int(fst.num_states())
+    return {"states": n, "arcs": int(sum(fst.num_arcs(s) for s in range(n)))}
+
+
 def measured_traffic(args):
     """DRAM bytes per string of the search kernel from the committed ncu capture of this workload (profiles/traffic.json)."""
     try:
@@ -316,6 +322,7 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step_device()
     tuples_per_string = float(d_nt.double().mean().item())
+    tuples_max = int(d_nt.max().item())
     occ = L.last_occupancy()
     state_bytes = tuples_per_string * 16 * min(batch, occ["resident"] or batch)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if state_bytes <= (1 << 30) else None
@@ -400,8 +407,9 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, batch, state_bytes, occ["resident"]),
         "composed_arcs_per_sec": value * relax_per_string,
-        "work_per_string": {"path_arcs": path_arcs, "tuples_run": tuples_per_string, "relax_run": relax_per_string,
-                            "mean_len": nbytes / batch},
+        "work_per_string": {"path_arcs": path_arcs, "tuples_run": tuples_per_string, "tuples_max": tuples_max,
+                            "relax_run": relax_per_string, "mean_len": nbytes / batch},
+        "transducer": transducer_size(fst),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": (traffic_ps * batch if traffic_ps else None), "peak_source": peak_src,
                      "kernel": "csp_batch_lean_kernel" if not args.engine or args.engine >= 2 else "csp_batch_warp_kernel",
