@@ -188,3 +188,19 @@ def test_trace_line_format(L):
                        env=dict(os.environ, LIBFST_TRACE_COMPOSE="1"))
     assert re.search(r"\[libfst\] sp_invalid_b op=fst_compose_frozen a=\d+ b=12345 in_states=2 in_arcs=1 "
                      r"out_states=0 out_arcs=0 elapsed_us=\d+", r.stderr), r.stderr
+
+
+def test_configure_validates_its_arguments(L):
+    """fst_b200_configure: engines 0..7, lanes 0/4/8/16/32, semantics 0/1; anything else is FST_INVALID_ARG and leaves
+    the previous configuration in place."""
+    try:
+        for engine in range(8):
+            L.configure(engine=engine)
+        for lanes in (0, 4, 8, 16, 32):
+            L.configure(lanes_per_string=lanes)
+        L.configure(semantics=L.EAGER)
+        for bad in (dict(engine=8), dict(lanes_per_string=5), dict(lanes_per_string=64), dict(semantics=2)):
+            with pytest.raises(ValueError):
+                L.configure(**bad)
+    finally:
+        L.configure()
