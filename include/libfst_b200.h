@@ -116,7 +116,12 @@ typedef enum {
                                epsilon loops (the reference runs out of memory here and
                                returns FST_INVALID_HANDLE); reported, never emitted      */
   FST_B200_TOO_LARGE = 3,   /* search state does not fit the configured device budget    */
-  FST_B200_INTERNAL = 4     /* engine self-check failed (never expected; report a bug)   */
+  FST_B200_INTERNAL = 4,    /* engine self-check failed (never expected; report a bug)   */
+  FST_B200_NOT_BYTES = 5    /* a best path was found and its arrays are valid, but its output
+                               tape holds a label above 256: it has no byte-string form
+                               (fst_print_output_string returns -1 for such a chain, string.zig:64-97);
+                               out_bytes of the string is empty; the pipeline entry does not feed
+                               it to the second stage                                      */
 } FstB200Status;
 
 /* Result of one batched call; all arrays are owned by the library and live in
@@ -161,6 +166,32 @@ FstError fst_compose_frozen_shortest_path_pipeline(FstHandle first, FstHandle se
                                                    const uint64_t* offsets, uint32_t n_strings,
                                                    FstB200BatchResult** out);
 
+/* One batch over several GPUs of the box (BASELINE north_star (3)).  The transducer is replicated (one
+ * device image per GPU, uploaded on first use), the batch is cut into contiguous chunks of roughly equal estimated
+ * cost, one host thread per GPU pulls chunks from an atomic queue and runs each as a host-buffer batch on its device
+ * (own stream; async D2H into the chunk's pinned result).  No collective: strings are independent.  The result lists
+ * the chunks IN INPUT ORDER: chunk k holds strings [chunk_first[k], chunk_first[k+1]) as an ordinary batch result
+ * (string i of the batch = string i - chunk_first[k] of its chunk), so nothing is copied a second time.
+ * `devices` == NULL or n_devices == 0: every visible device.  chunks_per_device == 0: default (2).  Errors as for the
+ * batch entry; an unknown or repeated device is FST_INVALID_ARG.  Per-string results do not depend on the device
+ * list (byte-identical for 1, 2, 4, 8 GPUs). */
+typedef struct {
+  uint32_t n_strings;
+  uint32_t n_chunks;
+  const uint64_t* chunk_first;              /* [n_chunks + 1] */
+  FstB200BatchResult* const* chunks;        /* [n_chunks] owned by this result (do not free them one by one) */
+  const int32_t* chunk_device;              /* [n_chunks] CUDA device that searched the chunk */
+  uint32_t n_devices;
+  double wall_ms;                           /* host wall time of the call */
+  double device_ms;                         /* largest per-device sum of the chunks' device times */
+  uint64_t total_tuples, total_relax;
+  uint32_t launches;
+} FstB200MultiResult;
+FstError fst_compose_frozen_shortest_path_batch_multi(FstHandle b, const uint8_t* bytes, const uint64_t* offsets,
+                                                      uint32_t n_strings, const int32_t* devices, uint32_t n_devices,
+                                                      uint32_t chunks_per_device, FstB200MultiResult** out);
+void fst_b200_multi_free(FstB200MultiResult* r);
+
 /* Eager lattices on the device: for every string i the result of
  * fst_compile_string(bytes_i) -> fst_compose_frozen(., b) of the reference (include/fst.h compose_frozen,
  * src/c-api.zig:675-742, src/ops/compose.zig:29-198) as CSR: states numbered in the reference's BFS discovery
@@ -190,10 +221,13 @@ void fst_b200_lattice_free(FstB200LatticeResult* r);
 
 /* Device-resident batch (inputs already in HBM; used for kernel-level timing and
  * for callers that keep a pipeline on the GPU).  All pointers are DEVICE pointers
- * on the current device; the call is asynchronous on `stream` (a cudaStream_t)
- * except when an oversized string forces a retry pass (then it synchronises).
- * Path arrays have capacity `path_capacity` arcs in total; if the batch needs more,
- * FST_OOM is returned and d_path_offsets[n] holds the required capacity. */
+ * on the current device.  The work is enqueued on `stream` (a cudaStream_t) and the
+ * call SYNCHRONISES that stream before it returns (the engine reads back which strings
+ * need a retry pass with larger search state, and the counters).  `max_len` is a hint:
+ * the longest string is measured on the device and the larger of the two sizes the
+ * search state.  Path arrays have capacity `path_capacity` arcs in total; if the batch
+ * needs more, FST_OOM is returned, the per-string outputs are undefined, and
+ * fst_b200_last_path_required() (same thread) gives the capacity to retry with. */
 typedef struct {
   int32_t* d_status;         /* [n]   */
   uint64_t* d_path_offsets;  /* [n+1] */
@@ -208,6 +242,16 @@ typedef struct {
 FstError fst_b200_batch_device(FstHandle b, const uint8_t* d_bytes, const uint64_t* d_offsets,
                                uint32_t n_strings, uint32_t max_len, const FstB200DeviceOut* out,
                                void* stream);
+/* Path arcs the last batched call on this thread produced or would have needed (see FST_OOM above). */
+uint64_t fst_b200_last_path_required(void);
+
+/* The EAGER pair per string, as its own entry point (BASELINE config 5): the result of
+ * fst_compile_string(bytes_i) -> fst_compose_frozen(., b) -> fst_shortest_path(., 1) of the reference
+ * (include/fst.h; src/ops/compose.zig:29-198 + src/ops/shortest-path.zig:18-139, whose tie-breaks differ from
+ * the lazy search's).  Same result layout as the batch entry; n_tuples = lattice states, total_relax = lattice
+ * arcs.  Finite non-negative weights only (other transducers: every string FST_B200_TOO_LARGE). */
+FstError fst_b200_compose_frozen_then_shortest_path_batch(FstHandle b, const uint8_t* bytes, const uint64_t* offsets,
+                                                          uint32_t n_strings, FstB200BatchResult** out);
 
 /* Bulk builders: same effect (and error codes) as repeated fst_mutable_add_state /
  * fst_mutable_set_final / fst_mutable_add_arc, under one lock.  Arcs are appended
@@ -232,7 +276,9 @@ typedef struct {
                                  string, a ready word of up to 32 tuples per step; table auto),
                                  5 = wave + hash table, 6 = wave + dense table, 7 = lean kernel
                                  (table auto); all produce identical output */
-  uint32_t semantics;         /* 0 = lazy: fst_compose_frozen_shortest_path (compose-shortest-path.zig);
+  uint32_t semantics;         /* DEFAULT of the batch entries that do not name their semantics (a test / bench knob;
+                                 production callers use fst_b200_compose_frozen_then_shortest_path_batch for the eager pair):
+                                 0 = lazy: fst_compose_frozen_shortest_path (compose-shortest-path.zig);
                                  1 = eager: the result of fst_compose_frozen followed by fst_shortest_path
                                  (compose.zig:29-198 + shortest-path.zig:18-139; other tie-breaks),
                                  n_tuples = lattice states, total_relax = lattice arcs; batched entry,

@@ -20,7 +20,7 @@ FST_OK, FST_OOM, FST_INVALID_ARG, FST_INVALID_STATE, FST_IO_ERROR = 0, 1, 2, 3, 
 FST_NO_STATE = 0xFFFFFFFF
 FST_EPSILON = 0
 FST_INVALID_HANDLE = 0xFFFFFFFFFFFFFFFF
-PATH, NO_PATH, CYCLE, TOO_LARGE, INTERNAL = 0, 1, 2, 3, 4
+PATH, NO_PATH, CYCLE, TOO_LARGE, INTERNAL, NOT_BYTES = 0, 1, 2, 3, 4, 5
 
 
 class FstArc(C.Structure):
@@ -41,6 +41,13 @@ class _BatchResult(C.Structure):
                 ("out_offsets", C.POINTER(C.c_uint64)), ("out_bytes", C.POINTER(C.c_uint8)),
                 ("device_ms", C.c_double), ("total_tuples", C.c_uint64), ("total_relax", C.c_uint64),
                 ("launches", C.c_uint32), ("passes", C.c_uint32)]
+
+
+class _MultiResult(C.Structure):
+    _fields_ = [("n_strings", C.c_uint32), ("n_chunks", C.c_uint32), ("chunk_first", C.POINTER(C.c_uint64)),
+                ("chunks", C.POINTER(C.POINTER(_BatchResult))), ("chunk_device", C.POINTER(C.c_int32)), ("n_devices", C.c_uint32),
+                ("wall_ms", C.c_double), ("device_ms", C.c_double), ("total_tuples", C.c_uint64), ("total_relax", C.c_uint64),
+                ("launches", C.c_uint32)]
 
 
 class DeviceOut(C.Structure):
@@ -86,6 +93,12 @@ EXPORTS = {
                                                             C.POINTER(C.POINTER(_BatchResult))]),
     "fst_compose_frozen_shortest_path_batch": (C.c_int, [C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32,
                                                          C.POINTER(C.POINTER(_BatchResult))]),
+    "fst_b200_compose_frozen_then_shortest_path_batch": (C.c_int, [C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32,
+                                                                   C.POINTER(C.POINTER(_BatchResult))]),
+    "fst_b200_last_path_required": (C.c_uint64, []),
+    "fst_compose_frozen_shortest_path_batch_multi": (C.c_int, [C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
+                                                               C.c_uint32, C.POINTER(C.POINTER(_MultiResult))]),
+    "fst_b200_multi_free": (None, [C.POINTER(_MultiResult)]),
     "fst_b200_batch_free": (None, [C.POINTER(_BatchResult)]),
     "fst_b200_compose_frozen_lattice_batch": (C.c_int, [C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32,
                                                         C.POINTER(C.POINTER(_LatticeResult))]),
@@ -330,34 +343,110 @@ def compose_frozen_shortest_path_pipeline(first: Fst, second: Fst, data: np.ndar
     return compose_frozen_shortest_path_batch(first, data, offsets, second=second)
 
 
-def compose_frozen_shortest_path_batch(b: Fst, data: np.ndarray, offsets: np.ndarray, copy: bool = True, second: Fst = None) -> BatchResult:
+def compose_frozen_then_shortest_path_batch(b: Fst, data: np.ndarray, offsets: np.ndarray) -> BatchResult:
+    """fst_b200_compose_frozen_then_shortest_path_batch: the eager pair per string (config 5), semantics per call."""
+    return compose_frozen_shortest_path_batch(b, data, offsets, eager=True)
+
+
+def compose_frozen_shortest_path_batch(b: Fst, data: np.ndarray, offsets: np.ndarray, copy: bool = True, second: Fst = None,
+                                       eager: bool = False) -> BatchResult:
     """fst_compose_frozen_shortest_path_batch over host buffers (`second`: the two-stage pipeline entry)."""
     data = np.ascontiguousarray(data, np.uint8)
     offsets = np.ascontiguousarray(offsets, np.uint64)
     n = len(offsets) - 1
     keep = data if data.size else np.zeros(1, np.uint8)
     out = C.POINTER(_BatchResult)()
-    if second is None:
+    if eager:
+        rc = lib().fst_b200_compose_frozen_then_shortest_path_batch(b.h, keep.ctypes.data, offsets.ctypes.data, n, C.byref(out))
+    elif second is None:
         rc = lib().fst_compose_frozen_shortest_path_batch(b.h, keep.ctypes.data, offsets.ctypes.data, n, C.byref(out))
     else:
         rc = lib().fst_compose_frozen_shortest_path_pipeline(b.h, second.h, keep.ctypes.data, offsets.ctypes.data, n, C.byref(out))
     if rc != FST_OK:
         raise RuntimeError(f"fst_compose_frozen_shortest_path_batch failed: FstError {rc}")
-    r = out.contents
     try:
-        def arr(ptr, cnt, dt):
-            if cnt == 0:
-                return np.zeros(0, dt)
-            a = np.ctypeslib.as_array(ptr, shape=(cnt,))
-            return a.astype(dt, copy=True)
-        poff = arr(r.path_offsets, n + 1, np.uint64)
-        ooff = arr(r.out_offsets, n + 1, np.uint64)
-        total, ototal = int(poff[-1]), int(ooff[-1])
-        return BatchResult(arr(r.status, n, np.int32), poff, arr(r.ilabels, total, np.uint32), arr(r.olabels, total, np.uint32),
-                           arr(r.weights, total, np.float64), arr(r.final_weights, n, np.float64), arr(r.n_tuples, n, np.uint32),
-                           ooff, arr(r.out_bytes, ototal, np.uint8), r.device_ms, r.total_tuples, r.total_relax, r.launches, r.passes)
+        return _copy_batch_result(out.contents, n)
     finally:
         lib().fst_b200_batch_free(out)
+
+
+def _copy_batch_result(r, n) -> BatchResult:
+    def arr(ptr, cnt, dt):
+        if cnt == 0:
+            return np.zeros(0, dt)
+        return np.ctypeslib.as_array(ptr, shape=(cnt,)).astype(dt, copy=True)
+    poff = arr(r.path_offsets, n + 1, np.uint64)
+    ooff = arr(r.out_offsets, n + 1, np.uint64)
+    total, ototal = int(poff[-1]), int(ooff[-1])
+    return BatchResult(arr(r.status, n, np.int32), poff, arr(r.ilabels, total, np.uint32), arr(r.olabels, total, np.uint32),
+                       arr(r.weights, total, np.float64), arr(r.final_weights, n, np.float64), arr(r.n_tuples, n, np.uint32),
+                       ooff, arr(r.out_bytes, ototal, np.uint8), r.device_ms, r.total_tuples, r.total_relax, r.launches, r.passes)
+
+
+@dataclass
+class MultiResult:
+    """fst_compose_frozen_shortest_path_batch_multi: the chunks in input order (each an ordinary BatchResult)."""
+    chunk_first: np.ndarray
+    chunk_device: np.ndarray
+    chunks: list
+    n_devices: int
+    wall_ms: float
+    device_ms: float
+    total_tuples: int
+    total_relax: int
+    launches: int
+
+    def flat(self) -> BatchResult:
+        """All chunks concatenated into one BatchResult (a host copy; tests compare this with the 1-GPU result)."""
+        if not self.chunks:
+            z = np.zeros(1, np.uint64)
+            return BatchResult(np.zeros(0, np.int32), z, np.zeros(0, np.uint32), np.zeros(0, np.uint32), np.zeros(0), np.zeros(0),
+                               np.zeros(0, np.uint32), z.copy(), np.zeros(0, np.uint8), 0.0, 0, 0, 0, 0)
+        poff, ooff, pb, ob = [np.zeros(1, np.uint64)], [np.zeros(1, np.uint64)], 0, 0
+        for c in self.chunks:
+            poff.append(c.path_offsets[1:] + np.uint64(pb)); ooff.append(c.out_offsets[1:] + np.uint64(ob))
+            pb += int(c.path_offsets[-1]); ob += int(c.out_offsets[-1])
+        cat = lambda f: np.concatenate([getattr(c, f) for c in self.chunks])   # noqa: E731
+        return BatchResult(cat("status"), np.concatenate(poff), cat("ilabels"), cat("olabels"), cat("weights"), cat("final_weights"),
+                           cat("n_tuples"), np.concatenate(ooff), cat("out_bytes"), self.device_ms, self.total_tuples, self.total_relax,
+                           self.launches, sum(c.passes for c in self.chunks))
+
+
+def compose_frozen_shortest_path_batch_multi(b: Fst, data: np.ndarray, offsets: np.ndarray, devices=None, chunks_per_device: int = 0,
+                                             copy: bool = True):
+    """fst_compose_frozen_shortest_path_batch_multi.  copy=False returns only the summary (counters, chunk layout) and frees
+    the native result at once (bench: the timed region must not include numpy copies)."""
+    data = np.ascontiguousarray(data, np.uint8)
+    offsets = np.ascontiguousarray(offsets, np.uint64)
+    n = len(offsets) - 1
+    keep = data if data.size else np.zeros(1, np.uint8)
+    dev = None if devices is None else np.ascontiguousarray(devices, np.int32)
+    out = C.POINTER(_MultiResult)()
+    rc = lib().fst_compose_frozen_shortest_path_batch_multi(b.h, keep.ctypes.data, offsets.ctypes.data, n,
+                                                            None if dev is None else dev.ctypes.data, 0 if dev is None else len(dev),
+                                                            chunks_per_device, C.byref(out))
+    if rc != FST_OK:
+        raise RuntimeError(f"fst_compose_frozen_shortest_path_batch_multi failed: FstError {rc}")
+    r = out.contents
+    try:
+        k = r.n_chunks
+        first = np.ctypeslib.as_array(r.chunk_first, shape=(k + 1,)).astype(np.uint64, copy=True)
+        cdev = np.ctypeslib.as_array(r.chunk_device, shape=(k,)).astype(np.int32, copy=True) if k else np.zeros(0, np.int32)
+        chunks = []
+        d2h = 0
+        for i in range(k):
+            c = r.chunks[i].contents
+            cn = int(first[i + 1] - first[i])
+            if copy:
+                chunks.append(_copy_batch_result(c, cn))
+            else:
+                pt, ot = int(c.path_offsets[cn]), int(c.out_offsets[cn])
+                d2h += cn * (4 + 8 + 4) + 2 * (cn + 1) * 8 + pt * 16 + ot
+        m = MultiResult(first, cdev, chunks, r.n_devices, r.wall_ms, r.device_ms, r.total_tuples, r.total_relax, r.launches)
+        m.d2h_bytes = d2h
+        return m
+    finally:
+        lib().fst_b200_multi_free(out)
 
 
 class LatticeBatch:

@@ -7,10 +7,12 @@
 // The search itself runs on the GPU; there is no CPU fallback.
 #include "../../include/libfst_b200.h"
 
+#include <atomic>
 #include <chrono>
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "engine.cuh"
@@ -175,7 +177,10 @@ static void pinned_release(void* p, size_t bytes) {
   if (!p) return;
   {
     std::lock_guard<std::mutex> lk(g_pin_mu);
-    if (g_pin_free.size() < 4) { g_pin_free.emplace_back(p, bytes); return; }
+    size_t held = 0;
+    for (auto& e : g_pin_free) held += e.second;
+    // one buffer per chunk of a multi-GPU call is recycled; the pool is bounded in entries and in bytes
+    if (g_pin_free.size() < 64 && held + bytes <= (48ull << 30)) { g_pin_free.emplace_back(p, bytes); return; }
   }
   cudaFreeHost(p);
 }
@@ -466,14 +471,15 @@ void fst_teardown(void) {
 }
 
 // ── batched entry points ──
+void fst_b200_batch_free(FstB200BatchResult* r);
 static int32_t map_status(int32_t s) {
   switch (s) { case kStPath: return FST_B200_PATH; case kStNoPath: return FST_B200_NO_PATH; case kStCycle: return FST_B200_CYCLE;
-               case kStInternal: return FST_B200_INTERNAL; default: return FST_B200_TOO_LARGE; }
+               case kStInternal: return FST_B200_INTERNAL; case kStNotBytes: return FST_B200_NOT_BYTES; default: return FST_B200_TOO_LARGE; }
 }
 
 // Host-buffer batch against one transducer (b2 == FST_INVALID_HANDLE) or the two-stage pipeline b then b2.
 static FstError host_batch(FstHandle b, FstHandle b2, const uint8_t* bytes, const uint64_t* offsets,
-                           uint32_t n_strings, FstB200BatchResult** out) {
+                           uint32_t n_strings, FstB200BatchResult** out, int semantics = -1) {
   if (!out) return FST_INVALID_ARG;
   *out = nullptr;
   if (!offsets || (!bytes && n_strings && offsets[n_strings] > 0)) return FST_INVALID_ARG;
@@ -522,9 +528,13 @@ static FstError host_batch(FstHandle b, FstHandle b2, const uint8_t* bytes, cons
     const Engine::IoBuffers& io = en->io();
     d_bytes = io.bytes; d_offsets = io.offsets; d_status = io.status; d_poff = io.path_offsets; d_il = io.il; d_ol = io.ol; d_w = io.w;
     d_fin = io.final_w; d_nt = io.n_tuples; d_ooff = io.out_offsets; d_obytes = io.out_bytes;
-    if (nbytes) cudaMemcpyAsync(d_bytes, bytes + offsets[0], nbytes, cudaMemcpyHostToDevice, stream);
-    cudaMemcpyAsync(d_offsets, rel.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, stream);
-    err = en->run_batch(img, d_bytes, d_offsets, n, (uint32_t)max_len, d_status, d_poff, d_il, d_ol, d_w, d_fin, d_nt, path_cap, d_ooff, d_obytes, path_cap, stream, &bc);
+    {
+      NvtxRange nvtx_h2d("fstb200 input H2D");
+      if (nbytes) cudaMemcpyAsync(d_bytes, bytes + offsets[0], nbytes, cudaMemcpyHostToDevice, stream);
+      cudaMemcpyAsync(d_offsets, rel.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, stream);
+    }
+    err = en->run_batch(img, d_bytes, d_offsets, n, (uint32_t)max_len, d_status, d_poff, d_il, d_ol, d_w, d_fin, d_nt, path_cap, d_ooff, d_obytes, path_cap, stream, &bc,
+                        nullptr, nullptr, semantics);
     if (err != cudaSuccess) { free_dev(); return err == cudaErrorMemoryAllocation ? FST_OOM : FST_INVALID_STATE; }
     // the flat path arrays were too small (the pool itself may have been large enough from an earlier call)
     const uint64_t need = std::max<uint64_t>(bc.path_required, bc.path_total);
@@ -548,7 +558,8 @@ static FstError host_batch(FstHandle b, FstHandle b2, const uint8_t* bytes, cons
       const Engine::IoBuffers& io = en->io(1);
       d_status = io.status; d_poff = io.path_offsets; d_il = io.il; d_ol = io.ol; d_w = io.w;
       d_fin = io.final_w; d_nt = io.n_tuples; d_ooff = io.out_offsets; d_obytes = io.out_bytes;
-      err = en->run_batch(img2, d_in2, d_off2, n, max_len2, d_status, d_poff, d_il, d_ol, d_w, d_fin, d_nt, path_cap, d_ooff, d_obytes, path_cap, stream, &bc, d_status1);
+      err = en->run_batch(img2, d_in2, d_off2, n, max_len2, d_status, d_poff, d_il, d_ol, d_w, d_fin, d_nt, path_cap, d_ooff, d_obytes, path_cap, stream, &bc, d_status1,
+                          nullptr, semantics);
       if (err != cudaSuccess) return err == cudaErrorMemoryAllocation ? FST_OOM : FST_INVALID_STATE;
       const uint64_t need = std::max<uint64_t>(bc.path_required, bc.path_total);
       if (need > path_cap && attempt < 4) { path_cap = need + need / 4 + 1024; continue; }
@@ -558,6 +569,7 @@ static FstError host_batch(FstHandle b, FstHandle b2, const uint8_t* bytes, cons
   }
   t_last = bc;
   // assemble the pinned host result
+  NvtxRange nvtx_d2h("fstb200 result D2H");
   const uint64_t total = bc.path_total;
   uint64_t out_total = 0;
   if (n) cudaMemcpy(&out_total, d_ooff + n, 8, cudaMemcpyDeviceToHost);
@@ -611,10 +623,133 @@ FstError fst_compose_frozen_shortest_path_batch(FstHandle b, const uint8_t* byte
   return host_batch(b, FST_INVALID_HANDLE, bytes, offsets, n_strings, out);
 }
 
+// Eager pair per call (BASELINE config 5): fst_compose_frozen then fst_shortest_path(., 1) of every string, as its own
+// entry point — the semantics are an argument of the call, not process state.
+FstError fst_b200_compose_frozen_then_shortest_path_batch(FstHandle b, const uint8_t* bytes, const uint64_t* offsets,
+                                                          uint32_t n_strings, FstB200BatchResult** out) {
+  return host_batch(b, FST_INVALID_HANDLE, bytes, offsets, n_strings, out, 1);
+}
+
 FstError fst_compose_frozen_shortest_path_pipeline(FstHandle first, FstHandle second, const uint8_t* bytes, const uint64_t* offsets,
                                                    uint32_t n_strings, FstB200BatchResult** out) {
   if (second == FST_INVALID_HANDLE) { if (out) *out = nullptr; return FST_INVALID_ARG; }
   return host_batch(first, second, bytes, offsets, n_strings, out);
+}
+
+// ── one batch over several GPUs (north_star (3)) ──
+// The transducer is replicated (one device image per GPU, uploaded on first use), the batch is cut into contiguous
+// chunks of roughly equal estimated cost, and one host thread per GPU pulls chunks from an atomic queue; every chunk
+// is an ordinary host-buffer batch on that thread's device (own stream, own engine, async D2H into the chunk's pinned
+// result).  No collective: strings are independent.  Output order = input order (chunks are contiguous and listed
+// in order; inside a chunk the batch entry keeps input order).
+struct MultiResultImpl {
+  FstB200MultiResult pub;
+  std::vector<uint64_t> first;
+  std::vector<FstB200BatchResult*> chunks;
+  std::vector<int32_t> device;
+};
+
+FstError fst_compose_frozen_shortest_path_batch_multi(FstHandle b, const uint8_t* bytes, const uint64_t* offsets, uint32_t n_strings,
+                                                      const int32_t* devices, uint32_t n_devices, uint32_t chunks_per_device,
+                                                      FstB200MultiResult** out) {
+  if (!out) return FST_INVALID_ARG;
+  *out = nullptr;
+  if (!offsets || (!bytes && n_strings && offsets[n_strings] > 0)) return FST_INVALID_ARG;
+  for (uint32_t i = 0; i < n_strings; i++) if (offsets[i + 1] < offsets[i]) return FST_INVALID_ARG;
+  int visible = 0;
+  if (cudaGetDeviceCount(&visible) != cudaSuccess || visible <= 0) {
+    cudaGetLastError();
+    std::fprintf(stderr, "[libfst_b200] no CUDA device: the batched search has no CPU fallback\n");
+    return FST_INVALID_STATE;
+  }
+  std::vector<int> devs;
+  if (n_devices == 0 || !devices) { for (int d = 0; d < visible; d++) devs.push_back(d); }
+  else {
+    for (uint32_t k = 0; k < n_devices; k++) {
+      if (devices[k] < 0 || devices[k] >= visible) return FST_INVALID_ARG;
+      for (int d : devs) if (d == devices[k]) return FST_INVALID_ARG;   // a device is listed once
+      devs.push_back(devices[k]);
+    }
+  }
+  // hold the handle for the whole call: a concurrent fst_free is deferred until the last chunk is done
+  FrozenEntry* fb;
+  { std::lock_guard<std::mutex> lk(g_mu); fb = g_frozen.pin(b); }
+  if (!fb) return FST_INVALID_ARG;
+  PinGuard pg{b};
+  if (fb->host->has_nan) return FST_INVALID_ARG;
+
+  auto* r = new (std::nothrow) MultiResultImpl();
+  if (!r) return FST_OOM;
+  // chunks of equal estimated cost (linear in the length: the search state of a string grows with its length)
+  if (chunks_per_device == 0) chunks_per_device = 2;
+  const uint64_t want_chunks = std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)devs.size() * chunks_per_device, n_strings));
+  r->first.push_back(0);
+  if (n_strings) {
+    const long double total_cost = (long double)(offsets[n_strings] - offsets[0]) + 16.0L * n_strings;
+    uint64_t next_cut = 1;
+    for (uint32_t i = 0; i < n_strings && next_cut < want_chunks; i++) {
+      const long double done = (long double)(offsets[i + 1] - offsets[0]) + 16.0L * (i + 1);
+      if (done * want_chunks >= total_cost * next_cut) {
+        if (i + 1 < n_strings && (uint64_t)(i + 1) > r->first.back()) r->first.push_back(i + 1);
+        next_cut++;
+      }
+    }
+    r->first.push_back(n_strings);
+  }
+  const uint32_t n_chunks = (uint32_t)r->first.size() - 1;
+  r->chunks.assign(n_chunks, nullptr);
+  r->device.assign(n_chunks, -1);
+  std::atomic<uint32_t> next{0};
+  std::atomic<int> first_err{FST_OK};
+  std::vector<double> dev_ms(devs.size(), 0.0);
+  std::vector<BatchCounters> dev_cnt(devs.size());
+  const auto t0 = std::chrono::steady_clock::now();
+  auto worker = [&](size_t w) {
+    if (cudaSetDevice(devs[w]) != cudaSuccess) { cudaGetLastError(); first_err = FST_INVALID_STATE; return; }
+    for (;;) {
+      const uint32_t k = next.fetch_add(1);
+      if (k >= n_chunks || first_err.load() != FST_OK) break;
+      const uint32_t lo = (uint32_t)r->first[k], hi = (uint32_t)r->first[k + 1];
+      FstB200BatchResult* res = nullptr;
+      const FstError e = host_batch(b, FST_INVALID_HANDLE, bytes, offsets + lo, hi - lo, &res);
+      if (e != FST_OK) { int expect = FST_OK; first_err.compare_exchange_strong(expect, (int)e); break; }
+      r->chunks[k] = res; r->device[k] = devs[w];
+      dev_ms[w] += res->device_ms;
+      dev_cnt[w].launches += res->launches; dev_cnt[w].passes += res->passes; dev_cnt[w].relax += res->total_relax; dev_cnt[w].tuples += res->total_tuples;
+    }
+  };
+  if (devs.size() == 1) {
+    int cur = 0; cudaGetDevice(&cur);
+    worker(0);
+    cudaSetDevice(cur);
+  } else {
+    std::vector<std::thread> th;
+    for (size_t w = 0; w < devs.size(); w++) th.emplace_back(worker, w);
+    for (auto& t : th) t.join();
+  }
+  if (first_err.load() != FST_OK) {
+    for (auto* c : r->chunks) fst_b200_batch_free(c);
+    delete r;
+    return (FstError)first_err.load();
+  }
+  r->pub.n_strings = n_strings; r->pub.n_chunks = n_chunks;
+  r->pub.chunk_first = r->first.data(); r->pub.chunks = r->chunks.data(); r->pub.chunk_device = r->device.data();
+  r->pub.n_devices = (uint32_t)devs.size();
+  r->pub.wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  r->pub.device_ms = 0; r->pub.total_relax = 0; r->pub.total_tuples = 0; r->pub.launches = 0;
+  for (size_t w = 0; w < devs.size(); w++) {
+    r->pub.device_ms = std::max(r->pub.device_ms, dev_ms[w]);
+    r->pub.total_relax += dev_cnt[w].relax; r->pub.total_tuples += dev_cnt[w].tuples; r->pub.launches += dev_cnt[w].launches;
+  }
+  *out = &r->pub;
+  return FST_OK;
+}
+
+void fst_b200_multi_free(FstB200MultiResult* r) {
+  if (!r) return;
+  auto* impl = reinterpret_cast<MultiResultImpl*>(r);   // pub is the first member
+  for (auto* c : impl->chunks) fst_b200_batch_free(c);
+  delete impl;
 }
 
 // ── eager lattices ──
@@ -756,6 +891,12 @@ FstError fst_b200_batch_device(FstHandle b, const uint8_t* d_bytes, const uint64
   if (!img) return err == cudaErrorMemoryAllocation ? FST_OOM : FST_INVALID_STATE;
   std::lock_guard<std::mutex> lk(en->mu);
   BatchCounters bc;
+  // the dense table is sized by the longest string: measure it (the caller's max_len is a hint; a longer string would
+  // write past its arena)
+  uint32_t measured = 0;
+  if (en->measure_max_len(d_offsets, n_strings, static_cast<cudaStream_t>(stream), &measured) != cudaSuccess) return FST_INVALID_STATE;
+  if (measured >= (1u << 30)) return FST_INVALID_ARG;
+  max_len = std::max(max_len, measured);
   err = en->run_batch(img, d_bytes, d_offsets, n_strings, max_len, o->d_status, o->d_path_offsets, o->d_ilabels, o->d_olabels, o->d_weights,
                       o->d_final_weights, o->d_n_tuples, o->path_capacity, nullptr, nullptr, 0, static_cast<cudaStream_t>(stream), &bc);
   t_last = bc;
@@ -773,6 +914,8 @@ FstError fst_b200_configure(const FstB200Config* cfg) {
   c.workspace_bytes = cfg->workspace_bytes; c.lanes_per_string = g; c.tuples_hint = cfg->tuples_hint; c.exhaustive = cfg->exhaustive; c.engine = cfg->engine; c.semantics = cfg->semantics;
   return FST_OK;
 }
+
+uint64_t fst_b200_last_path_required(void) { return std::max<uint64_t>(t_last.path_required, t_last.path_total); }
 
 void fst_b200_last_occupancy(uint32_t* resident, uint32_t* capacity) {
   if (resident) *resident = t_last.resident;

@@ -599,7 +599,8 @@ __global__ void csp_emit_kernel(EmitParams e) {
   const uint32_t warps_per_block = blockDim.x >> 5;
   const uint32_t lane = threadIdx.x & 31u;
   for (uint32_t i = blockIdx.x * warps_per_block + (threadIdx.x >> 5); i < e.n_strings; i += gridDim.x * warps_per_block) {
-    if (e.status[i] != kStPath) continue;
+    if (e.status[i] != kStPath && e.status[i] != kStNotBytes) continue;
+    const bool bytes_ok = e.status[i] == kStPath;
     uint32_t n = e.path_len[i];
     uint64_t src = e.pool_off[i], dst = e.path_offsets[i];
     if (dst + n > e.path_capacity) continue;
@@ -612,7 +613,7 @@ __global__ void csp_emit_kernel(EmitParams e) {
         a = e.pool[src + (n - 1 - k)];
         e.ilabels[dst + k] = a.ilabel; e.olabels[dst + k] = a.olabel; e.weights[dst + k] = a.weight;
       }
-      if (e.out_bytes) {
+      if (e.out_bytes && bytes_ok) {
         unsigned m = __ballot_sync(0xFFFFFFFFu, valid && a.olabel != 0);
         if (valid && a.olabel != 0) e.out_bytes[ob + __popc(m & ((1u << lane) - 1u))] = (uint8_t)(a.olabel - 1u);
         ob += __popc(m);
@@ -622,18 +623,21 @@ __global__ void csp_emit_kernel(EmitParams e) {
 }
 
 // Output-tape byte count per string (for the exclusive scan that places out_bytes).
-__global__ void csp_count_out_kernel(const int32_t* status, const uint32_t* path_len, const uint64_t* pool_off,
+// A path with an output label above 256 has no byte form: its status becomes kStNotBytes, its output string is empty.
+__global__ void csp_count_out_kernel(int32_t* status, const uint32_t* path_len, const uint64_t* pool_off,
                                      const PoolArc* pool, uint32_t n_strings, uint32_t* out_len) {
   const uint32_t warps_per_block = blockDim.x >> 5;
   const uint32_t lane = threadIdx.x & 31u;
   for (uint32_t i = blockIdx.x * warps_per_block + (threadIdx.x >> 5); i < n_strings; i += gridDim.x * warps_per_block) {
     uint32_t cnt = 0;
+    bool wide = false;
     if (status[i] == kStPath) {
       uint32_t n = path_len[i]; uint64_t src = pool_off[i];
-      for (uint32_t k = lane; k < n; k += 32) cnt += pool[src + k].olabel != 0;
+      for (uint32_t k = lane; k < n; k += 32) { const uint32_t ol = pool[src + k].olabel; cnt += ol != 0; wide |= ol > 256u; }
     }
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
-    if (lane == 0) out_len[i] = cnt;
+    wide = __any_sync(0xFFFFFFFFu, wide);
+    if (lane == 0) { out_len[i] = wide ? 0u : cnt; if (wide) status[i] = kStNotBytes; }
   }
 }
 

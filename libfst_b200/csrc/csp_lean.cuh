@@ -94,6 +94,7 @@ __host__ __device__ inline LeanLayout lean_layout(int G, bool dense, uint64_t ta
   LeanLayout L;
   auto al = [](uint64_t x) { return (x + 127) & ~127ull; };
   const uint32_t ids_per_line = 32u * (uint32_t)G;
+  tuple_cap += 8;   // slack: the fast kernel checks the capacity once per step (a step creates at most 8 tuples)
   const uint32_t lines = (tuple_cap + ids_per_line - 1) / ids_per_line;
   L.n1 = (lines + 31) / 32;
   L.tab_bytes = al(tab_entries * (dense ? (crec ? 8ull : 16ull) : 32ull));
@@ -178,7 +179,8 @@ struct LeanState {
 //   dense table: index P * dense_stride + SF; id -> key array holds the COMPACT 32-bit form
 //                (P << key_sbits) | SF  (fits: the dense table has < 2^30 records).
 // Table kind (template parameter DENSE of everything below): 0 = hash table of 32-byte slots, 1 = dense table of
-// 16-byte records {dist f64, id, prev}, 2 = dense table of COMPACT 8-byte records  dist:20 | id:22 | prev:22  for
+// 16-byte records {dist f64, id, prev}, 2 = dense table of COMPACT 8-byte records  dist:20 | prev:22 | id:22  (most
+// significant first: the relax rule "take iff (new dist, popped id) < (dist, prev)" is ONE unsigned compare of the top 42 bits)  for
 // transducers whose weights are all small non-negative integers (every distance is then an integer, exact in
 // both forms): half the table bytes per string, so more strings fit HBM and a DRAM sector holds four records.
 // All-ones = never touched in every kind.  A distance that does not fit 20 bits marks the string for a retry with
@@ -226,8 +228,8 @@ __device__ __forceinline__ void lean_lookup(const SearchParams& p, const LeanCtx
                                             uint32_t& id, uint32_t& prev) {
   if (DENSE >= 2) {
     pos = lean_dense_pos(p, P, SF);
-    const uint2 v = *reinterpret_cast<const uint2*>(c.base + (uint64_t)pos * 8);   // x = low word: id:10 low bits | prev:22 ; y = dist:20 | id:12 high bits
-    const uint32_t i = ((v.y & 0xFFFu) << 10) | (v.x >> 22), pr = v.x & kCrecNone;
+    const uint2 v = *reinterpret_cast<const uint2*>(c.base + (uint64_t)pos * 8);   // x = low word: prev:10 low bits | id:22 ; y = dist:20 | prev:12 high bits
+    const uint32_t i = v.x & kCrecNone, pr = ((v.y & 0xFFFu) << 10) | (v.x >> 22);
     id = i == kCrecNone ? kNone : (DENSE == 3 ? ((i & (kCrecBfsBit - 1u)) | ((i & kCrecBfsBit) ? kBfsFlag : 0u)) : i);
     prev = pr == kCrecNone ? kNone : pr;
     dist = (i == kCrecNone || (v.y >> 12) == 0xFFFFFu) ? d_inf() : (double)(v.y >> 12);
@@ -273,7 +275,7 @@ __device__ __forceinline__ void lean_store(const LeanCtx& c, uint32_t pos, uint3
   if (DENSE >= 2) {
     const uint32_t d = d_isinf(dist) ? 0xFFFFFu : __double2uint_rn(fmin(dist, kCrecMaxDist)), pr = prev & kCrecNone;   // kNone -> kCrecNone
     const uint32_t i = DENSE == 3 ? ((id & (kCrecBfsBit - 1u)) | ((id & kBfsFlag) ? kCrecBfsBit : 0u)) : id;
-    *reinterpret_cast<uint2*>(c.base + (uint64_t)pos * 8) = make_uint2((i << 22) | pr, (d << 12) | ((i >> 10) & 0xFFFu));
+    *reinterpret_cast<uint2*>(c.base + (uint64_t)pos * 8) = make_uint2((pr << 22) | (i & kCrecNone), (d << 12) | ((pr >> 10) & 0xFFFu));
     return;
   }
   const uint4 v = make_uint4((uint32_t)__double2loint(dist), (uint32_t)__double2hiint(dist), id, prev);

@@ -48,6 +48,10 @@ struct DevFstView {
   // bigidx[(n * 257 + label)] = {first arc, arc count} of the state's arcs with that ilabel (label 0 = the
   // input-epsilon prefix), so that an expansion fetches only the few arcs that can match.  null: not built.
   const uint2* bigidx;
+  // integer copy of the leader slab for transducers whose weights are all integers in 0..4095 (fast kernel,
+  // csp_fast.cuh): same records with z = weight << 12 (the distance field of the compact table record) and w = 0,
+  // plus one all-idle row at index num_states that groups without a string read.  null: not built.
+  const uint4* islab;
 };
 
 // General (non-linear) left operand as CSR in STORED arc order
@@ -79,7 +83,9 @@ constexpr uint32_t kSettledBit = 0x80000000u;
 
 // Per-string status written by the search kernel (internal; the C ABI maps
 // kRetry to a retry pass and finally to FST_B200_TOO_LARGE).
-enum : int32_t { kStPath = 0, kStNoPath = 1, kStCycle = 2, kStTooLarge = 3, kStInternal = 4, kStRetry = 100, kStRetryHeap = 101, kStRetryWide = 102 };
+// kStNotBytes: a path was found (path arrays are valid) but its output tape holds a label above 256, so it has no
+// byte-string form (the reference's fst_print_output_string returns -1 for such a chain).
+enum : int32_t { kStPath = 0, kStNoPath = 1, kStCycle = 2, kStTooLarge = 3, kStInternal = 4, kStNotBytes = 5, kStRetry = 100, kStRetryHeap = 101, kStRetryWide = 102 };
 
 // Reversed path arc as written to the path pool by the search kernel.
 struct __align__(16) PoolArc { uint32_t ilabel, olabel; double weight; };

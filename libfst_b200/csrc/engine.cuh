@@ -6,6 +6,7 @@
 #pragma once
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <nvtx3/nvToolsExt.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -18,6 +19,7 @@
 #include "csp_kernels.cuh"
 #include "csp_warp.cuh"
 #include "csp_lean.cuh"
+#include "csp_fast.cuh"
 #include "csp_wave.cuh"
 #include "host_fst.hpp"
 
@@ -32,6 +34,9 @@ namespace fstb200 {
       return _e;                                                                                \
     }                                                                                           \
   } while (0)
+
+// NVTX range over a scope (nsys timeline of a call: upload / search pass / emit / D2H; header-only, no-op without a tool).
+struct NvtxRange { explicit NvtxRange(const char* name) { nvtxRangePushA(name); } ~NvtxRange() { nvtxRangePop(); } };
 
 struct Config {
   uint64_t workspace_bytes = 0;
@@ -53,6 +58,7 @@ struct DeviceFst {
   void* wslab_block = nullptr;  // leader-only fixed-stride search records (lean kernel with 8 lanes, wave kernel), may be null
   void* wslab4_block = nullptr; // ... 4 records per state (lean kernel with 4 lanes), built for sparse transducers only
   void* bigidx_block = nullptr; // label index of the states the leader slab cannot hold, may be null
+  void* islab_block = nullptr;  // integer leader slab (fast kernel), may be null
   bool int_weights = false;     // every finite arc / final weight is a non-negative integer <= 4095: compact 8-byte table records apply
   bool wave_ok = false;         // wave slab built and at least 90 % of the states fit it
   size_t bytes = 0;
@@ -65,6 +71,7 @@ struct DeviceFst {
 };
 
 inline cudaError_t upload_fst(const HostFrozen& f, int device, DeviceFst** out) {
+  NvtxRange nvtx_upload("fstb200 upload_fst");
   *out = nullptr;
   const uint32_t S = f.num_states(), A = f.num_arcs();
   const ImgState* st = f.states(); const ImgArc* ar = f.all_arcs();
@@ -95,7 +102,9 @@ inline cudaError_t upload_fst(const HostFrozen& f, int device, DeviceFst** out) 
   }
   // search records: group the arcs of a state by (ilabel, nextstate); arcs are ilabel-sorted, so a group
   // lives inside one ilabel run
-  const bool lean_ok = !f.has_negative && all_finite && S < (1u << 31);
+  // (an image whose ilabel runs are not in the full freeze order — accepted by fromBytes — takes the literal
+  // serial-relax kernel: the parallel-arc fold and the back-track's first-tight-arc recovery assume that order)
+  const bool lean_ok = !f.has_negative && all_finite && S < (1u << 31) && f.fully_sorted;
   if (lean_ok) {
     std::unordered_map<uint32_t, uint32_t> first_of;   // nextstate -> first arc of the current ilabel run
     for (uint32_t s = 0; s < S; s++) {
@@ -128,7 +137,7 @@ inline cudaError_t upload_fst(const HostFrozen& f, int device, DeviceFst** out) 
     if (!std::isinf(st[s].final_weight)) int_weights = st[s].final_weight >= 0.0 && st[s].final_weight <= 4095.0 && st[s].final_weight == std::floor(st[s].final_weight);
   auto d = new DeviceFst();
   d->int_weights = int_weights;
-  d->device = device; d->bytes = total; d->serial = f.has_negative; d->lean_ok = lean_ok;
+  d->device = device; d->bytes = total; d->serial = f.has_negative || !f.fully_sorted; d->lean_ok = lean_ok;
   cudaError_t e = cudaMalloc(&d->block, total);
   if (e != cudaSuccess) { delete d; return e; }
   e = cudaMemcpy(d->block, h.data(), total, cudaMemcpyHostToDevice);
@@ -162,7 +171,7 @@ inline cudaError_t upload_fst(const HostFrozen& f, int device, DeviceFst** out) 
       cudaGetLastError(); cudaFree(d->slab_block); d->slab_block = nullptr;
     }
   }
-  d->view.wslab = nullptr; d->view.wslab4 = nullptr; d->view.bigidx = nullptr;
+  d->view.wslab = nullptr; d->view.wslab4 = nullptr; d->view.bigidx = nullptr; d->view.islab = nullptr;
   if (lean_ok && (uint64_t)S * kWaveSlots * 16 <= (256ull << 20)) {
     std::vector<uint4> ws((size_t)S * kWaveSlots, make_uint4(0xFFFFFFFFu, 0u, 0u, 0u));
     uint32_t n_big = 0;
@@ -258,6 +267,27 @@ inline cudaError_t upload_fst(const HostFrozen& f, int device, DeviceFst** out) 
     } else if (use4) {
       cudaGetLastError(); cudaFree(d->wslab4_block); d->wslab4_block = nullptr;
     }
+    // integer leader slab of the fast kernel (csp_fast.cuh): weight pre-shifted to the distance field of the compact
+    // table record; marker rows keep their label-index number; one all-idle row at index S
+    d->view.islab = nullptr;
+    if (int_weights && d->view.wslab && S < (1u << 30)) {
+      std::vector<uint4> is((size_t)(S + 1) * kWaveSlots, make_uint4(0xFFFFFFFFu, 0u, 0u, 0u));
+      for (size_t k = 0; k < (size_t)S * kWaveSlots; k++) {
+        uint4 r = ws[k];
+        if (r.x != 0xFFFFFFFFu && r.x != kWaveBig) {   // {ilabel, next << 1 | epsilon, weight << 12, arcs folded}
+          double w; unsigned long long wb = ((unsigned long long)r.w << 32) | r.z; std::memcpy(&w, &wb, 8);
+          const uint32_t il = r.x & 0xFFFFu;
+          r = make_uint4(il, (r.y << 1) | (il == 0u ? 1u : 0u), (uint32_t)w << 12, r.x >> 16);
+        }
+        is[k] = r;
+      }
+      if (cudaMalloc(&d->islab_block, is.size() * 16) == cudaSuccess &&
+          cudaMemcpy(d->islab_block, is.data(), is.size() * 16, cudaMemcpyHostToDevice) == cudaSuccess) {
+        d->view.islab = static_cast<const uint4*>(d->islab_block);
+      } else {
+        cudaGetLastError(); cudaFree(d->islab_block); d->islab_block = nullptr;
+      }
+    }
   }
   *out = d;
   return cudaSuccess;
@@ -271,6 +301,7 @@ inline void free_device_fst(DeviceFst* d) {
   cudaFree(d->wslab_block);
   cudaFree(d->bigidx_block);
   cudaFree(d->wslab4_block);
+  cudaFree(d->islab_block);
   if (cur != d->device) cudaSetDevice(cur);
   delete d;
 }
@@ -306,6 +337,16 @@ __global__ void length_keys_kernel(const uint64_t* offsets, uint32_t n, uint32_t
 __global__ void widen_kernel(const uint32_t* in, uint64_t* out, uint32_t n) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = in[i];
+}
+// Longest string of a device-resident batch (fst_b200_batch_device: the caller's max_len is only a hint).
+__global__ void max_len_kernel(const uint64_t* offsets, uint32_t n, uint32_t* out) {
+  uint32_t m = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint64_t d = offsets[i + 1] - offsets[i];
+    m = max(m, d > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)d);
+  }
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
 }
 __global__ void max_u32_kernel(const uint32_t* in, uint32_t n, uint32_t* out) {
   uint32_t m = 0;
@@ -368,7 +409,8 @@ class Engine {
                         int32_t* d_status, uint64_t* d_path_offsets, uint32_t* d_il, uint32_t* d_ol, double* d_w,
                         double* d_final, uint32_t* d_ntuples, uint64_t path_capacity,
                         uint64_t* d_out_offsets, uint8_t* d_out_bytes, uint64_t out_capacity,
-                        cudaStream_t stream, BatchCounters* bc, const int32_t* d_skip = nullptr, LatticeOut* lat = nullptr) {
+                        cudaStream_t stream, BatchCounters* bc, const int32_t* d_skip = nullptr, LatticeOut* lat = nullptr,
+                        int semantics = -1) {   // -1: the configured default; 0 lazy; 1 eager (per call, see c_api.cu)
     *bc = BatchCounters();
     if (n == 0) {
       FSTB_CUDA(cudaMemsetAsync(d_path_offsets, 0, 8, stream));
@@ -376,6 +418,7 @@ class Engine {
       return cudaStreamSynchronize(stream);
     }
     Config cfg = global_config();
+    if (semantics >= 0) cfg.semantics = (uint32_t)semantics;
     if (lat) cfg.semantics = 1;   // the lattice is the eager pair's (compose.zig numbering)
     FSTB_CUDA(ensure_scratch(n, path_capacity));
     if (lat) {
@@ -476,7 +519,7 @@ class Engine {
         const LeanLayout L = lean_layout((int)gm.G, gm.dense, gm.tab_entries, gm.tuple_cap, gm.heap_cap, gm.crec);
         p.off_keyof = L.off_keyof; p.off_l0 = L.off_l0; p.off_chunks = L.off_chunks;
         p.n1 = L.n1; p.smem_words = gm.smem_per_group / 4; p.dense_stride = fst->view.num_states * 2u;
-        p.key_sbits = 1; while ((1u << p.key_sbits) < p.dense_stride) p.key_sbits++;
+        p.key_sbits = 1; while ((1u << p.key_sbits) < p.dense_stride + (gm.fast ? 2u : 0u)) p.key_sbits++;   // fast kernel: room for the idle row S
         p.eager = cfg.semantics == 1 ? 1u : 0u;
       }
       p.queue_head = d_cnt + 0;
@@ -493,7 +536,10 @@ class Engine {
       }
       p.status = d_status; p.path_len = d_path_len_; p.pool_off = d_pool_off_; p.final_w = d_final; p.n_tuples = d_ntuples;
       p.pool = d_pool_; p.pool_cap = pool_cap_;
-      launch_search(gm, blocks, threads, p, stream);
+      {
+        NvtxRange r("fstb200 search pass");
+        launch_search(gm, blocks, threads, p, stream);
+      }
       bc->launches++;
       FSTB_CUDA(cudaGetLastError());
       // any string that overflowed its arena (or the pool)?
@@ -511,8 +557,8 @@ class Engine {
         if (gm.kind == kWave) std::fprintf(stderr, "[libfst_b200] wave stats (cumulative): chunk steps %llu, tuples popped by chunks %llu, single-pop steps %llu, abandoned chunks %llu\n", ws[0], ws[1], ws[2], ws[3]);
       }
       if (std::getenv("LIBFST_B200_DEBUG"))
-        std::fprintf(stderr, "[libfst_b200] segment %u/%zu (max_len %u) pass %u kind %d G %u dense %d eager %d tuple_cap %u heap_cap %u items %u groups %u retry %u heap_retry %u\n",
-                     seg_no, segs.size(), seg_max_len, pass, gm.kind, gm.G, (int)gm.dense + (int)gm.crec, (int)gm.eager, gm.tuple_cap, gm.heap_cap, n_items, blocks * gpb, retry, heap_retry);
+        std::fprintf(stderr, "[libfst_b200] segment %u/%zu (max_len %u) pass %u kind %d fast %d G %u dense %d eager %d tuple_cap %u heap_cap %u items %u groups %u retry %u heap_retry %u\n",
+                     seg_no, segs.size(), seg_max_len, pass, gm.kind, (int)gm.fast, gm.G, (int)gm.dense + (int)gm.crec, (int)gm.eager, gm.tuple_cap, gm.heap_cap, n_items, blocks * gpb, retry, heap_retry);
       unsigned long long pool_used; std::memcpy(&pool_used, hc + 2, 8);
       if (retry == 0) break;
       if (pool_used > pool_cap_) {
@@ -546,6 +592,7 @@ class Engine {
     }
 
     // ordered output: offsets = exclusive scan of path lengths, then un-reverse
+    NvtxRange nvtx_emit("fstb200 emit");
     widen_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_path_len_, d_len64_, n);
     FSTB_CUDA(cudaMemsetAsync(d_len64_ + n, 0, 8, stream));
     size_t tmp = scan_tmp_bytes_;
@@ -607,9 +654,15 @@ class Engine {
     if (S) std::memcpy(h.data() + o_fin, fin.data(), (size_t)S * 8);
     if (A) { std::memcpy(h.data() + o_il, ail.data(), (size_t)A * 4); std::memcpy(h.data() + o_ol, aol.data(), (size_t)A * 4);
              std::memcpy(h.data() + o_w, aw.data(), (size_t)A * 8); std::memcpy(h.data() + o_nx, anx.data(), (size_t)A * 4); }
-    uint8_t* d_lhs = nullptr;
-    FSTB_CUDA(cudaMalloc(&d_lhs, total));
-    struct Guard { uint8_t* p; ~Guard() { cudaFree(p); } } guard{d_lhs};
+    // device copy of the left operand: engine-owned, grow-only (a cudaMalloc + cudaFree per call is most of the
+    // latency of a small single call)
+    if (total > lhs_cap_) {
+      cudaFree(d_lhs_); d_lhs_ = nullptr; lhs_cap_ = 0;
+      const size_t want = total + total / 2 + 4096;
+      FSTB_CUDA(cudaMalloc(&d_lhs_, want));
+      lhs_cap_ = want;
+    }
+    uint8_t* d_lhs = d_lhs_;
     FSTB_CUDA(cudaMemcpyAsync(d_lhs, h.data(), total, cudaMemcpyHostToDevice, stream));
     const uint64_t path_capacity = 1u << 16;
     FSTB_CUDA(ensure_scratch(1, path_capacity));
@@ -697,7 +750,7 @@ class Engine {
   // set 0: the batch entry (and stage 1 of the pipeline entry); set 1: stage 2 of the pipeline entry
   cudaError_t ensure_io(uint32_t n, uint64_t nbytes, uint64_t path_cap, int set = 0) {
     IoBuffers& io_ = io_sets_[set];
-    if (n > io_.cap_n) {
+    if (n > io_.cap_n || io_.offsets == nullptr) {
       cudaFree(io_.offsets); cudaFree(io_.status); cudaFree(io_.path_offsets); cudaFree(io_.final_w); cudaFree(io_.n_tuples); cudaFree(io_.out_offsets);
       io_.offsets = nullptr; io_.status = nullptr; io_.path_offsets = nullptr; io_.final_w = nullptr; io_.n_tuples = nullptr; io_.out_offsets = nullptr;
       io_.cap_n = 0;
@@ -707,13 +760,13 @@ class Engine {
       FSTB_CUDA(cudaMalloc(&io_.n_tuples, m * 4 + 16)); FSTB_CUDA(cudaMalloc(&io_.out_offsets, (m + 1) * 8));
       io_.cap_n = m;
     }
-    if (nbytes > io_.cap_bytes) {
+    if (nbytes > io_.cap_bytes || io_.bytes == nullptr) {
       cudaFree(io_.bytes); io_.bytes = nullptr; io_.cap_bytes = 0;
       const uint64_t m = nbytes + nbytes / 8 + 256;
       FSTB_CUDA(cudaMalloc(&io_.bytes, m + 16));
       io_.cap_bytes = m;
     }
-    if (path_cap > io_.cap_path) {
+    if (path_cap > io_.cap_path || io_.il == nullptr) {
       cudaFree(io_.il); cudaFree(io_.ol); cudaFree(io_.w); cudaFree(io_.out_bytes);
       io_.il = io_.ol = nullptr; io_.w = nullptr; io_.out_bytes = nullptr; io_.cap_path = 0;
       const uint64_t m = path_cap + path_cap / 8 + 256;
@@ -731,10 +784,22 @@ class Engine {
       io_ = IoBuffers();
     }
     cudaFree(d_workspace_); d_workspace_ = nullptr; workspace_bytes_ = 0; layout_groups_ = 0; budget_cache_ = 0;
+    cudaFree(d_lhs_); d_lhs_ = nullptr; lhs_cap_ = 0;
     free_scratch();
   }
 
   uint64_t pool_capacity() const { return pool_cap_; }
+
+  // Longest string of a device-resident batch (synchronises the stream).
+  cudaError_t measure_max_len(const uint64_t* d_offsets, uint32_t n, cudaStream_t stream, uint32_t* out) {
+    uint32_t* d_cnt = static_cast<uint32_t*>(d_small_);
+    FSTB_CUDA(cudaMemsetAsync(d_cnt + 11, 0, 4, stream));
+    if (n) max_len_kernel<<<std::min<uint32_t>((n + 255) / 256, 592), 256, 0, stream>>>(d_offsets, n, d_cnt + 11);
+    FSTB_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(h_small_) + 128, d_cnt + 11, 4, cudaMemcpyDeviceToHost, stream));
+    FSTB_CUDA(cudaStreamSynchronize(stream));
+    *out = *reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(h_small_) + 128);
+    return cudaSuccess;
+  }
 
   // Longest output-tape string of the last run_batch that produced output bytes (pipeline: stage 2's max_len).
   cudaError_t last_max_out_len(uint32_t n, cudaStream_t stream, uint32_t* out) {
@@ -763,15 +828,16 @@ class Engine {
   void* d_sort_tmp_ = nullptr; size_t sort_tmp_bytes_ = 0;
 
   uint32_t init_launches_ = 0;
+  uint8_t* d_lhs_ = nullptr; size_t lhs_cap_ = 0;   // single-call left operand (run_general)
 
   enum { kSerial = 0, kWarp = 1, kLean = 2, kWave = 3 };
   // Arena geometry of one pass: which kernel, and every capacity that shapes the arena.
   struct Geom {
-    int kind = kWarp; uint32_t G = 32; bool dense = false, slab = false, eager = false, crec = false; uint64_t tab_entries = 0;
+    int kind = kWarp; uint32_t G = 32; bool dense = false, slab = false, eager = false, crec = false, fast = false; uint64_t tab_entries = 0;
     uint32_t hash_cap = 0, tuple_cap = 0, heap_cap = 0, bag_cap = 0, smem_per_group = 0; uint64_t stride = 0;
     uint64_t off_l0 = 0, tab_bytes = 0, l0_bytes = 0;
     bool same(const Geom& o) const {
-      return kind == o.kind && G == o.G && dense == o.dense && crec == o.crec && slab == o.slab && tab_entries == o.tab_entries && hash_cap == o.hash_cap &&
+      return kind == o.kind && G == o.G && dense == o.dense && crec == o.crec && slab == o.slab && fast == o.fast && tab_entries == o.tab_entries && hash_cap == o.hash_cap &&
              tuple_cap == o.tuple_cap && heap_cap == o.heap_cap && bag_cap == o.bag_cap && stride == o.stride;
     }
   };
@@ -813,7 +879,7 @@ class Engine {
     g->eager = cfg.semantics == 1;
     const uint64_t E = (uint64_t)(max_len + 1) * fst->view.num_states * 2;
     // compact 8-byte records: lean kernel, integer weights, ids below 2^22 - 1 (eager: 2^21 - 1, one bit is the BFS flag)
-    const bool crec = crec_ok && !wave && std::min<uint64_t>(tuple_cap, E) < (cfg.semantics == 1 ? kCrecBfsBit - 1u : kCrecNone) &&
+    const bool crec = crec_ok && !wave && std::min<uint64_t>(tuple_cap, E) + 8 < (cfg.semantics == 1 ? kCrecBfsBit - 1u : kCrecNone) &&
                       std::getenv("LIBFST_B200_NO_CREC") == nullptr;
     const uint64_t rec_bytes = crec ? 8 : 16;
     const bool dense_ok = E < 0xFFFFFF00ull && E * rec_bytes <= kDenseLimitBytes;
@@ -833,6 +899,10 @@ class Engine {
       if ((uint64_t)tuple_cap > E) tuple_cap = (uint32_t)E;
       g->tab_entries = E; g->hash_cap = 0;
       g->crec = crec && g->kind == kLean;
+      // fast kernel (csp_fast.cuh): 8 lanes on the integer leader slab, compact records, lazy semantics
+      uint32_t sb = 1; while ((1ull << sb) < (uint64_t)fst->view.num_states * 2 + 2) sb++;
+      g->fast = g->crec && g->G == 8 && g->slab && !g->eager && fst->view.islab != nullptr && ((uint64_t)(max_len + 2) << sb) < 0xFFFFFFF0ull &&
+                std::getenv("LIBFST_B200_NO_FAST") == nullptr;
     } else {
       g->hash_cap = (uint32_t)std::min<uint64_t>(0xFFFFFFF0ull, (uint64_t)tuple_cap * 100 / 65 + 16);
       g->tab_entries = g->hash_cap;
@@ -870,7 +940,7 @@ class Engine {
   }
   static const void* kernel_ptr(const Geom& g) {
     if (g.kind == kWarp) return (const void*)csp_batch_warp_kernel;
-    if (g.kind == kLean) return lean_kernel_ptr(g);
+    if (g.kind == kLean) return g.fast ? (const void*)csp_batch_fast_kernel : lean_kernel_ptr(g);
     if (g.kind == kWave) return g.dense ? (const void*)csp_batch_wave_kernel<true> : (const void*)csp_batch_wave_kernel<false>;
     switch (g.G) { case 32: return (const void*)csp_batch_kernel<32, true>; case 16: return (const void*)csp_batch_kernel<16, true>;
                    case 8: return (const void*)csp_batch_kernel<8, true>; default: return (const void*)csp_batch_kernel<4, true>; }
@@ -893,6 +963,11 @@ class Engine {
   static void launch_search(const Geom& g, uint32_t blocks, uint32_t threads, const SearchParams& p, cudaStream_t s) {
     const size_t sm = (size_t)(threads / g.G) * g.smem_per_group;
     if (g.kind == kWarp) { csp_batch_warp_kernel<<<blocks, threads, sm, s>>>(p); return; }
+    if (g.kind == kLean && g.fast) {
+      cudaMemcpyToSymbolAsync(c_fp, &p, sizeof(SearchParams), 0, cudaMemcpyHostToDevice, s);   // pageable source: staged before the call returns
+      csp_batch_fast_kernel<<<blocks, threads, sm, s>>>();
+      return;
+    }
     if (g.kind == kLean || g.kind == kWave) {
       void* args[] = {const_cast<SearchParams*>(&p)};
       cudaLaunchKernel(kernel_ptr(g), dim3(blocks), dim3(threads), args, sm, s);
@@ -952,11 +1027,13 @@ class Engine {
     d_status1_ = nullptr; d_final1_ = nullptr; d_pool_ = nullptr; d_scan_tmp_ = nullptr; scratch_n_ = 0; pool_cap_ = 0; scan_tmp_bytes_ = 0;
   }
   cudaError_t ensure_scratch(uint32_t n, uint64_t pool_cap) {
-    if (n > scratch_n_) {
-      cudaFree(d_path_len_); cudaFree(d_pool_off_); cudaFree(d_out_len_); cudaFree(d_len64_); cudaFree(d_order_buf_[0]); cudaFree(d_order_buf_[1]);
-      cudaFree(d_status1_); cudaFree(d_final1_); cudaFree(d_scan_tmp_);
-      cudaFree(d_sort_keys_[0]); cudaFree(d_sort_keys_[1]); cudaFree(d_sort_vals_[0]); cudaFree(d_sort_vals_[1]); cudaFree(d_sort_tmp_);
-      uint32_t m = n + n / 8 + 16;
+    if (n > scratch_n_ || d_path_len_ == nullptr) {
+      // free, null and zero the capacities first: a failed allocation below must not leave stale pointers behind
+      const uint64_t keep_pool = pool_cap_;
+      PoolArc* pool = d_pool_; d_pool_ = nullptr; pool_cap_ = 0;
+      free_scratch();
+      d_pool_ = pool; pool_cap_ = keep_pool;
+      const uint32_t m = n + n / 8 + 16;
       FSTB_CUDA(cudaMalloc(&d_path_len_, (size_t)m * 4)); FSTB_CUDA(cudaMalloc(&d_pool_off_, (size_t)m * 8));
       FSTB_CUDA(cudaMalloc(&d_out_len_, (size_t)m * 4)); FSTB_CUDA(cudaMalloc(&d_len64_, (size_t)(m + 1) * 8));
       FSTB_CUDA(cudaMalloc(&d_order_buf_[0], (size_t)m * 4)); FSTB_CUDA(cudaMalloc(&d_order_buf_[1], (size_t)m * 4));
@@ -964,16 +1041,15 @@ class Engine {
       size_t tmp = 0;
       FSTB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, (uint64_t*)nullptr, (uint64_t*)nullptr, (int)(m + 1)));
       FSTB_CUDA(cudaMalloc(&d_scan_tmp_, tmp + 256));
-      scan_tmp_bytes_ = tmp + 256;
       for (int k = 0; k < 2; k++) { FSTB_CUDA(cudaMalloc(&d_sort_keys_[k], (size_t)m * 4)); FSTB_CUDA(cudaMalloc(&d_sort_vals_[k], (size_t)m * 4)); }
       size_t st = 0;
       FSTB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, st, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)m, 0, 32));
       FSTB_CUDA(cudaMalloc(&d_sort_tmp_, st + 256));
-      sort_tmp_bytes_ = st + 256;
-      scratch_n_ = m;
+      scan_tmp_bytes_ = tmp + 256; sort_tmp_bytes_ = st + 256;
+      scratch_n_ = m;   // only now: every buffer of this size exists
     }
     if (pool_cap > pool_cap_) {
-      cudaFree(d_pool_);
+      cudaFree(d_pool_); d_pool_ = nullptr; pool_cap_ = 0;
       FSTB_CUDA(cudaMalloc(&d_pool_, (size_t)pool_cap * sizeof(PoolArc)));
       pool_cap_ = pool_cap;
     }

@@ -109,6 +109,8 @@ class HostFrozen {
   size_t nbytes = 0;
   bool has_nan = false;
   bool has_negative = false;      // any arc or final weight < 0 (incl. -inf): non-monotone search
+  bool fully_sorted = true;       // every state's arcs are in the full freeze order (src/arc.zig:46-54); fromBytes only
+                                  // checks the ilabels (src/fst.zig:227-273), so a loaded image may not be
   uint32_t max_out_degree = 0;
 
   const uint8_t* bytes() const { return reinterpret_cast<const uint8_t*>(storage.data()); }
@@ -137,6 +139,14 @@ class HostFrozen {
       double w = ar[i].weight;
       if (std::isnan(w)) has_nan = true;
       if (w < 0) has_negative = true;
+    }
+    fully_sorted = true;
+    for (uint32_t i = 0; i < num_states() && fully_sorted; i++) {
+      const ImgArc* a = ar + st[i].arc_offset;
+      for (uint32_t j = 1; j < st[i].num_arcs; j++) {
+        const HostArc x{a[j - 1].ilabel, a[j - 1].olabel, a[j - 1].weight, a[j - 1].nextstate}, y{a[j].ilabel, a[j].olabel, a[j].weight, a[j].nextstate};
+        if (arc_less(y, x)) { fully_sorted = false; break; }
+      }
     }
   }
 

@@ -190,8 +190,6 @@ def test_golden_fixtures_on_gpu(L, O, gpu):
     from libfst_b200 import synth
     names = {0: "plain", 1: "epsilon_dense", 2: "ambiguous"}
     for row in fx["rows"]:
-        if row["kind"] == 1 and row["L"] > 33:
-            continue
         f = synth.TRANSDUCERS[names[row["kind"]]](row["T"], row["B"]).freeze()
         s = synth.input_string(names[row["kind"]], row["L"], row["B"])
         data, offsets = L.pack_strings([s])
