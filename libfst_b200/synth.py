@@ -155,3 +155,46 @@ def wetext_strings(sources, n: int, seed: int = 1, lo: int = 11, hi: int = 251):
         else:
             out.append(bytes(rng.integers(32, 127, L).astype(np.uint8)))
     return out
+
+
+def wetext_packed(sources, n: int, seed: int = 1, lo: int = 11, hi: int = 251, block: int = 1 << 17):
+    """The same distribution as wetext_strings, vectorised for large batches: (uint8 data, uint64 offsets[n + 1]).
+    Dictionary strings are grown in rounds (every string still shorter than its target length L appends one random
+    dictionary source per round), random strings are uniform printable bytes; generated block by block so that the
+    index arrays stay small.  Deterministic in (sources, n, seed, lo, hi, block)."""
+    rng = np.random.default_rng(seed)
+    src_len = np.fromiter((len(s) for s in sources), np.int64, len(sources))
+    src_off = np.zeros(len(sources) + 1, np.int64); np.cumsum(src_len, out=src_off[1:])
+    src_bytes = np.frombuffer(b"".join(sources), np.uint8)
+    datas, lens_all = [], []
+    for b0 in range(0, n, block):
+        m = min(block, n - b0)
+        Ls = rng.integers(lo, hi + 1, m).astype(np.int64)
+        is_dict = rng.random(m) < 0.7
+        tot = np.zeros(m, np.int64)
+        tok_str, tok_src, tok_pos = [], [], []
+        active = np.flatnonzero(is_dict)
+        while active.size:
+            pick = rng.integers(0, len(sources), active.size)
+            tok_str.append(active); tok_src.append(pick); tok_pos.append(tot[active].copy())
+            tot[active] += src_len[pick]
+            active = active[tot[active] < Ls[active]]
+        lens = np.where(is_dict, tot, Ls)
+        off = np.zeros(m + 1, np.int64); np.cumsum(lens, out=off[1:])
+        data = np.empty(int(off[-1]), np.uint8)
+        # uniform printable bytes for the other strings
+        rid = np.flatnonzero(~is_dict)
+        if rid.size:
+            rl = lens[rid]
+            start = np.repeat(off[rid], rl)
+            within = np.arange(int(rl.sum()), dtype=np.int64) - np.repeat(np.cumsum(rl) - rl, rl)
+            data[start + within] = rng.integers(32, 127, int(rl.sum())).astype(np.uint8)
+        if tok_str:
+            ts, tsrc, tpos = np.concatenate(tok_str), np.concatenate(tok_src), np.concatenate(tok_pos)
+            sl = src_len[tsrc]
+            within = np.arange(int(sl.sum()), dtype=np.int64) - np.repeat(np.cumsum(sl) - sl, sl)
+            data[np.repeat(off[ts] + tpos, sl) + within] = src_bytes[np.repeat(src_off[tsrc], sl) + within]
+        datas.append(data); lens_all.append(lens)
+    lens = np.concatenate(lens_all) if lens_all else np.zeros(0, np.int64)
+    offsets = np.zeros(n + 1, np.uint64); np.cumsum(lens.astype(np.uint64), out=offsets[1:])
+    return (np.concatenate(datas) if datas else np.zeros(0, np.uint8)), offsets
