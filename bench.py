@@ -294,7 +294,8 @@ def measured_traffic(args):
     """DRAM / L2 bytes per string of the search kernel from the committed ncu capture of this workload
     (profiles/traffic.json, written by scripts/traffic.py from `ncu --metrics dram__bytes_*`): NOT measured in this run."""
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(traffic_key(args))
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(traffic_key(args))
+        return t if isinstance(t, dict) else None
     except Exception:
         return None
 

@@ -176,7 +176,7 @@ struct LeanState {
 // Tuple key of the lean path as a (P, SF) pair: P = string position, SF = (transducer state << 1) | filter
 // (filter is 0 or 1 for an epsilon-free left operand; states < 2^31 is checked at upload).
 //   hash table:  64-bit key (P << 32) | SF.
-//   dense table: index P * dense_stride + SF; id -> key array holds the COMPACT 32-bit form
+//   dense table: index lean_dense_pos(P, SF) (position-major or diagonal rows); id -> key array holds the COMPACT 32-bit form
 //                (P << key_sbits) | SF  (fits: the dense table has < 2^30 records).
 // Table kind (template parameter DENSE of everything below): 0 = hash table of 32-byte slots, 1 = dense table of
 // 16-byte records {dist f64, id, prev}, 2 = dense table of COMPACT 8-byte records  dist:20 | prev:22 | id:22  (most
@@ -210,7 +210,7 @@ __device__ __forceinline__ void lean_keyof_load(const SearchParams& p, const Lea
 // sector.  (A filter-major index, which makes the match targets of one expansion contiguous, was measured:
 // L1 hit rate 55 % -> 43 %, DRAM reads x2.8; the variants are touched close together in time.)
 __device__ __forceinline__ uint32_t lean_dense_pos(const SearchParams& p, uint32_t P, uint32_t SF) {
-  return P * p.dense_stride + SF;
+  return SF * p.pos_h + ((SF & 1u) ? p.pos_k : 0u) + p.pos_c + P * p.pos_m2;   // see SearchParams::pos_h
 }
 // Hash of a tuple key for the open-addressing table: two odd multipliers and an xorshift-multiply finisher (the slot is
 // taken from the HIGH bits).  Keys are structured (small positions, clustered state numbers).  Against the 64-bit

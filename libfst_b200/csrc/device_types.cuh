@@ -115,7 +115,20 @@ struct SearchParams {
   uint64_t off_keyof, off_l0, off_chunks;
   uint32_t n1;             // ready-bitmap summary words
   uint32_t smem_words;     // shared-memory words per group
-  uint32_t dense_stride;   // 2 * S: dense index = p * dense_stride + ((s << 1) | filter)
+  uint32_t dense_stride;   // 2 * S (bits of the compact id -> key form)
+  // dense table index of tuple (P, SF = state << 1 | filter), an affine map (mod 2^32):
+  //     pos = SF * pos_h + (filter ? pos_k : 0) + pos_c + P * pos_m2
+  //   position-major (pos_h 1, pos_k 0, pos_m2 2S, pos_c 0):   pos = P * 2S + SF   — a row per string position
+  //   diagonal(skew) (pos_h H = half row of max_len + 2 records padded to a whole number of 32-byte sectors, pos_k 1,
+  //   pos_m2 1 - skew 2H, pos_c skew max_len 2H):
+  //                                   pos = ((state - skew P + skew max_len) * 2 + filter) * H + P + filter
+  //   — a row per DIAGONAL state - skew * position, the two filter variants in separate half rows.  On a chain-like
+  //   transducer with input-epsilon arcs the reference's pop order runs along such diagonals (engine.cuh,
+  //   DeviceFst::layout_skew): a chain of pops (position + k, state + k skew) and its match targets walk along a few
+  //   half rows 8 bytes per step; the filter-1 half row (the epsilon target sits at the popped position, the match
+  //   targets at the next one) is shifted by one record and the half rows are sector-padded, so that all streams
+  //   enter a new 32-byte sector in the same step: one DRAM round trip every fourth pop of a chain instead of every pop.
+  uint32_t pos_h, pos_m2, pos_c, pos_k;
   uint32_t key_sbits;      // dense: bits of ((s << 1) | filter) in the compact id -> key array
   uint32_t eager;          // lean path: 1 = eager semantics (compose() then shortestPath(), BASELINE config 5)
   // work queue + counters

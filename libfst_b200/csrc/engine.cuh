@@ -67,6 +67,8 @@ struct DeviceFst {
   uint32_t hint_tuples = 0;  // largest per-string tuple count seen so far (arena sizing)
   uint32_t hint_heap_mult = 1;  // radix-heap pool depth that sufficed so far (lean kernel)
   bool crec_failed = false;     // a search outgrew the compact records once: do not try them again
+  int layout_skew = -1;         // dense table layout: -1 = a row per string position; >= 0 = a row per diagonal
+                                // state - skew * position (chain-like transducers with input-epsilon arcs, see upload_fst)
   uint32_t lean_lanes = 32;     // lanes per string of the lean kernel: smallest of 8/16/32 that covers 90% of the states' arcs in one step
 };
 
@@ -153,6 +155,39 @@ inline cudaError_t upload_fst(const HostFrozen& f, int device, DeviceFst** out) 
     uint32_t le8 = 0, le16 = 0;
     for (uint32_t s = 0; s < S; s++) { le8 += st[s].num_arcs <= 8; le16 += st[s].num_arcs <= 16; }
     d->lean_lanes = (uint64_t)le8 * 10 >= (uint64_t)S * 9 ? 8 : ((uint64_t)le16 * 10 >= (uint64_t)S * 9 ? 16 : 32);
+  }
+  // Dense table layout.  On a chain-like transducer (arcs lead a bounded number of states forward) WITH input-epsilon
+  // arcs, the reference's pop order keeps running along the cheapest match arcs: a tuple first met through a dearer arc
+  // is lowered by the cheapest arc of its predecessor, gets ready with its old (small) id and is popped next, and so on
+  // — chains (position + k, state + k * skew), skew = the state advance of the cheapest match arcs.  With a table row
+  // per diagonal  state - skew * position  such a chain and its targets walk along a few rows (the next pop's records
+  // sit in the sectors the last pop fetched); with a row per position every pop lands in another row.  Measured on
+  // eps-dense (skew 1), 1 B200: len 33 39.1 k -> 54.3 k strings/s, len 96 13.8 k -> 15.4 k, len 251 2.33 k -> 2.70 k;
+  // skew 0 = 13.6 k, skew 2 = 12.9 k at len 96 (profiles/README.md).  Without input-epsilon arcs every arc advances the
+  // position and the front is a position (ambiguous chain: rows 3.60 M, diagonals 1.87 M strings/s): a row per
+  // position.  Pure layout choice: any skew gives the same results (tests/test_gpu_literal.py::test_dense_table_layouts).
+  {
+    double wmin_m = std::numeric_limits<double>::infinity();
+    for (uint32_t a = 0; a < A; a++)
+      if (ar[a].ilabel != 0 && ar[a].ilabel <= 256u) wmin_m = std::min(wmin_m, ar[a].weight);
+    uint64_t n_arcs = 0, out = 0, eps_states = 0, hist[66] = {0};
+    for (uint32_t s = 0; s < S; s++) {
+      bool has_eps = false;
+      for (uint32_t a = st[s].arc_offset; a < st[s].arc_offset + st[s].num_arcs; a++) {
+        if (ar[a].ilabel > 256u) continue;
+        const int64_t dl = (int64_t)ar[a].nextstate - (int64_t)s;
+        n_arcs++;
+        if (dl < 0 || dl > 64) out++;
+        if (ar[a].ilabel == 0) has_eps = true;
+        else if (ar[a].weight == wmin_m && dl >= 0 && dl <= 64) hist[dl]++;
+      }
+      eps_states += has_eps;
+    }
+    int best = 0;
+    for (int k = 1; k <= 64; k++) if (hist[k] > hist[best]) best = k;
+    if (n_arcs > 0 && out * 20 <= n_arcs && eps_states * 2 >= S && hist[best] > 0) d->layout_skew = best;
+    if (const char* e = std::getenv("LIBFST_B200_SKEW")) d->layout_skew = std::atoi(e);   // experiments / tests: -1, 0, 1, ...
+    if (d->layout_skew > 64) d->layout_skew = 64;
   }
   d->view.slab = nullptr; d->view.slab_lanes = 0; d->view.pad0 = 0;
   const uint32_t GL = d->lean_lanes == 8 ? 16 : d->lean_lanes;   // 8 lanes read the leader slab (below); this one serves 16 / 32
@@ -519,6 +554,13 @@ class Engine {
         const LeanLayout L = lean_layout((int)gm.G, gm.dense, gm.tab_entries, gm.tuple_cap, gm.heap_cap, gm.crec);
         p.off_keyof = L.off_keyof; p.off_l0 = L.off_l0; p.off_chunks = L.off_chunks;
         p.n1 = L.n1; p.smem_words = gm.smem_per_group / 4; p.dense_stride = fst->view.num_states * 2u;
+        if (gm.skew < 0) { p.pos_h = 1u; p.pos_m2 = p.dense_stride; p.pos_c = 0u; p.pos_k = 0u; }
+        else {
+          // pos = ((state - skew P + skew max_len) * 2 + filter) * H + P + filter      (H = padded half row)
+          const uint32_t H = diag_half_row(seg_max_len), W = 2u * H;
+          p.pos_h = H; p.pos_c = (uint32_t)gm.skew * seg_max_len * W; p.pos_m2 = 1u - (uint32_t)gm.skew * W;
+          p.pos_k = diag_shift() ? 1u : 0u;
+        }
         p.key_sbits = 1; while ((1u << p.key_sbits) < p.dense_stride + (gm.fast ? 2u : 0u)) p.key_sbits++;   // fast kernel: room for the idle row S
         p.eager = cfg.semantics == 1 ? 1u : 0u;
       }
@@ -557,8 +599,8 @@ class Engine {
         if (gm.kind == kWave) std::fprintf(stderr, "[libfst_b200] wave stats (cumulative): chunk steps %llu, tuples popped by chunks %llu, single-pop steps %llu, abandoned chunks %llu\n", ws[0], ws[1], ws[2], ws[3]);
       }
       if (std::getenv("LIBFST_B200_DEBUG"))
-        std::fprintf(stderr, "[libfst_b200] segment %u/%zu (max_len %u) pass %u kind %d fast %d G %u dense %d eager %d tuple_cap %u heap_cap %u items %u groups %u retry %u heap_retry %u\n",
-                     seg_no, segs.size(), seg_max_len, pass, gm.kind, (int)gm.fast, gm.G, (int)gm.dense + (int)gm.crec, (int)gm.eager, gm.tuple_cap, gm.heap_cap, n_items, blocks * gpb, retry, heap_retry);
+        std::fprintf(stderr, "[libfst_b200] segment %u/%zu (max_len %u) pass %u kind %d fast %d skew %d G %u dense %d eager %d tuple_cap %u heap_cap %u items %u groups %u retry %u heap_retry %u\n",
+                     seg_no, segs.size(), seg_max_len, pass, gm.kind, (int)gm.fast, gm.skew, gm.G, (int)gm.dense + (int)gm.crec, (int)gm.eager, gm.tuple_cap, gm.heap_cap, n_items, blocks * gpb, retry, heap_retry);
       unsigned long long pool_used; std::memcpy(&pool_used, hc + 2, 8);
       if (retry == 0) break;
       if (pool_used > pool_cap_) {
@@ -833,16 +875,25 @@ class Engine {
   enum { kSerial = 0, kWarp = 1, kLean = 2, kWave = 3 };
   // Arena geometry of one pass: which kernel, and every capacity that shapes the arena.
   struct Geom {
-    int kind = kWarp; uint32_t G = 32; bool dense = false, slab = false, eager = false, crec = false, fast = false; uint64_t tab_entries = 0;
+    int kind = kWarp; uint32_t G = 32; bool dense = false, slab = false, eager = false, crec = false, fast = false; int skew = -1; uint64_t tab_entries = 0;
     uint32_t hash_cap = 0, tuple_cap = 0, heap_cap = 0, bag_cap = 0, smem_per_group = 0; uint64_t stride = 0;
     uint64_t off_l0 = 0, tab_bytes = 0, l0_bytes = 0;
     bool same(const Geom& o) const {
-      return kind == o.kind && G == o.G && dense == o.dense && crec == o.crec && slab == o.slab && fast == o.fast && tab_entries == o.tab_entries && hash_cap == o.hash_cap &&
+      return kind == o.kind && G == o.G && dense == o.dense && crec == o.crec && slab == o.slab && fast == o.fast && skew == o.skew && tab_entries == o.tab_entries && hash_cap == o.hash_cap &&
              tuple_cap == o.tuple_cap && heap_cap == o.heap_cap && bag_cap == o.bag_cap && stride == o.stride;
     }
   };
   static constexpr uint64_t kDenseLimitBytes = 96ull << 20;   // per-string dense table budget
   Geom layout_;
+
+  // Diagonal layout: records of one filter variant per row (one per string position, the filter-1 half shifted by one
+  // record), padded to whole 32-byte sectors: the row streams of a chain of pops then cross their sector boundaries in
+  // the SAME step (see SearchParams::pos_h).
+  static bool diag_shift() { static const bool v = std::getenv("LIBFST_B200_SHIFT") != nullptr; return v; }
+  static uint32_t diag_half_row(uint32_t max_len) {
+    static const int pad = std::getenv("LIBFST_B200_HPAD") ? std::atoi(std::getenv("LIBFST_B200_HPAD")) : 0;
+    return max_len + 1u + (diag_shift() ? 1u : 0u) + (uint32_t)pad;
+  }
 
   static bool geometry(const Config& cfg, const DeviceFst* fst, uint32_t max_len, uint32_t tuple_cap, uint32_t heap_mult, Geom* g, bool crec_ok = false,
                        uint64_t budget = 0) {
@@ -877,7 +928,13 @@ class Engine {
     if (wave) { g->kind = kWave; g->G = 32; }
     g->slab = g->G == 8 ? fst->view.wslab != nullptr : (g->G == 4 ? fst->view.wslab4 != nullptr : fst->view.slab_lanes == g->G);
     g->eager = cfg.semantics == 1;
-    const uint64_t E = (uint64_t)(max_len + 1) * fst->view.num_states * 2;
+    // dense records: a row per position, or a row per diagonal when that costs at most 25 % more records
+    uint64_t E = (uint64_t)(max_len + 1) * fst->view.num_states * 2;
+    g->skew = -1;
+    if (fst->layout_skew >= 0) {
+      const uint64_t Ed = ((uint64_t)fst->view.num_states + (uint64_t)fst->layout_skew * max_len) * 2 * diag_half_row(max_len);
+      if (Ed * 4 <= E * 5) { E = Ed; g->skew = fst->layout_skew; }
+    }
     // compact 8-byte records: lean kernel, integer weights, ids below 2^22 - 1 (eager: 2^21 - 1, one bit is the BFS flag)
     const bool crec = crec_ok && !wave && std::min<uint64_t>(tuple_cap, E) + 8 < (cfg.semantics == 1 ? kCrecBfsBit - 1u : kCrecNone) &&
                       std::getenv("LIBFST_B200_NO_CREC") == nullptr;
@@ -901,7 +958,7 @@ class Engine {
       g->crec = crec && g->kind == kLean;
       // fast kernel (csp_fast.cuh): 8 lanes on the integer leader slab, compact records, lazy semantics
       uint32_t sb = 1; while ((1ull << sb) < (uint64_t)fst->view.num_states * 2 + 2) sb++;
-      g->fast = g->crec && g->G == 8 && g->slab && !g->eager && fst->view.islab != nullptr && ((uint64_t)(max_len + 2) << sb) < 0xFFFFFFF0ull &&
+      g->fast = g->crec && g->G == 8 && g->slab && fst->view.islab != nullptr && ((uint64_t)(max_len + 2) << sb) < 0xFFFFFFF0ull &&
                 std::getenv("LIBFST_B200_NO_FAST") == nullptr;
     } else {
       g->hash_cap = (uint32_t)std::min<uint64_t>(0xFFFFFFF0ull, (uint64_t)tuple_cap * 100 / 65 + 16);
@@ -940,7 +997,7 @@ class Engine {
   }
   static const void* kernel_ptr(const Geom& g) {
     if (g.kind == kWarp) return (const void*)csp_batch_warp_kernel;
-    if (g.kind == kLean) return g.fast ? (const void*)csp_batch_fast_kernel : lean_kernel_ptr(g);
+    if (g.kind == kLean) return g.fast ? (g.eager ? (const void*)csp_batch_fast_kernel<true> : (const void*)csp_batch_fast_kernel<false>) : lean_kernel_ptr(g);
     if (g.kind == kWave) return g.dense ? (const void*)csp_batch_wave_kernel<true> : (const void*)csp_batch_wave_kernel<false>;
     switch (g.G) { case 32: return (const void*)csp_batch_kernel<32, true>; case 16: return (const void*)csp_batch_kernel<16, true>;
                    case 8: return (const void*)csp_batch_kernel<8, true>; default: return (const void*)csp_batch_kernel<4, true>; }
@@ -965,7 +1022,7 @@ class Engine {
     if (g.kind == kWarp) { csp_batch_warp_kernel<<<blocks, threads, sm, s>>>(p); return; }
     if (g.kind == kLean && g.fast) {
       cudaMemcpyToSymbolAsync(c_fp, &p, sizeof(SearchParams), 0, cudaMemcpyHostToDevice, s);   // pageable source: staged before the call returns
-      csp_batch_fast_kernel<<<blocks, threads, sm, s>>>();
+      if (g.eager) csp_batch_fast_kernel<true><<<blocks, threads, sm, s>>>(); else csp_batch_fast_kernel<false><<<blocks, threads, sm, s>>>();
       return;
     }
     if (g.kind == kLean || g.kind == kWave) {

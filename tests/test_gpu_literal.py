@@ -335,3 +335,41 @@ def test_semantics_per_call_and_concurrent_callers(L, O, gpu):
                 il, ol, w = g.path(0)
                 assert np.array_equal(il, want.ilabels) and np.array_equal(ol, want.olabels)
         assert L.lib().fst_num_states(h) == 0            # the handle is dead afterwards
+
+
+@pytest.mark.parametrize("skew", ["-1", "0", "3", "7"])
+def test_dense_table_layouts(L, O, gpu, skew):
+    """The dense table's index map (a row per string position, or a row per diagonal state - skew * position) is a pure
+    layout choice: every skew must give the oracle's results — fast kernel, general lean kernel, 16-byte records and
+    the eager kernels.  LIBFST_B200_SKEW overrides the upload heuristic (read when a handle is first searched)."""
+    from common import assert_batch_matches_eager_oracle
+    rng = random.Random(31 + int(skew))
+    img = gen_image(O, 1, 512, 12)
+    forc = O.Frozen.from_bytes(img)
+    strings = [bytes(n) for n in (33, 0, 1, 19, 40, 7)]
+    specs = [random_rhs(rng, max_states=8, real=(k % 3 == 2)) for k in range(12)]
+    rstrings = [random_string(rng, max_len=9) for _ in range(30)]
+    os.environ["LIBFST_B200_SKEW"] = skew
+    try:
+        for no_fast in (False, True):
+            if no_fast:
+                os.environ["LIBFST_B200_NO_FAST"] = "1"
+            for exhaustive in (0, 1):
+                L.configure(exhaustive=exhaustive)
+                assert_batch_matches_oracle(L, O, L.Fst.from_image(img), forc, strings)
+            L.configure(engine=3, lanes_per_string=16)
+            assert_batch_matches_oracle(L, O, L.Fst.from_image(img), forc, strings)
+            L.configure()
+            for spec in specs:
+                fprod, fo, _ = frozen_pair(L, O, spec)
+                assert_batch_matches_oracle(L, O, fprod, fo, rstrings)
+        f = L.Fst.from_image(img)
+        data, offsets = L.pack_strings(strings)
+        assert_batch_matches_eager_oracle(L, O, f, forc, strings, res=L.compose_frozen_then_shortest_path_batch(f, data, offsets))
+        # mixed lengths in one batch: every string uses the rows of the longest
+        amb = gen_image(O, 2, 4096, 12)
+        assert_batch_matches_oracle(L, O, L.Fst.from_image(amb), O.Frozen.from_bytes(amb), [bytes(n) for n in (96, 5, 64, 0, 33)])
+    finally:
+        os.environ.pop("LIBFST_B200_SKEW", None)
+        os.environ.pop("LIBFST_B200_NO_FAST", None)
+        L.configure()
