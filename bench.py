@@ -62,6 +62,8 @@ def parse(argv=None):
     ap.add_argument("--total", type=int, default=0, help="--scaling strong: strings of the one batch (0 = workload default)")
     ap.add_argument("--distinct", type=int, default=1 << 20, help="wetext, --scaling strong: distinct strings generated (tiled up to --total)")
     ap.add_argument("--chunks-per-device", type=int, default=0)
+    ap.add_argument("--bytes-only", action="store_true",
+                    help="--scaling strong: FST_B200_RESULT_NO_PATHS (output strings, statuses, path lengths; no per-arc arrays in the D2H)")
     ap.add_argument("--workload", default="epsilon_dense", choices=sorted(WORKLOADS))
     ap.add_argument("--len", type=int, default=96)
     ap.add_argument("--transducer-len", type=int, default=4096)
@@ -431,19 +433,20 @@ def run_strong(args):
     L.configure(lanes_per_string=args.lanes, exhaustive=args.exhaustive, engine=args.engine, tuples_hint=args.tuples_hint,
                 semantics=L.EAGER if args.semantics == "eager" else L.LAZY)
     devices = list(range(args.gpus))
+    rflags = L.RESULT_NO_PATHS if args.bytes_only else 0
     total = args.total or {"epsilon_dense": 1 << 18, "ambiguous": 1 << 21, "plain": 1 << 22, "wetext": 10000000}[args.workload]
     fst, data, offsets, max_len, oracle_loader, sources = make_workload(args, total, seed=1)
     nbytes = int(offsets[-1])
     # warm-up: images uploaded, arenas sized, pinned result buffers in the pool
     for _ in range(max(1, min(args.warmup, 2))):
-        L.compose_frozen_shortest_path_batch_multi(fst, data, offsets, devices=devices, chunks_per_device=args.chunks_per_device, copy=False)
+        L.compose_frozen_shortest_path_batch_multi(fst, data, offsets, devices=devices, chunks_per_device=args.chunks_per_device, copy=False, flags=rflags)
     samplers = [ClockSampler(d) for d in devices[:1]]
     for s in samplers:
         s.start()
     wall, dev_ms, launches, relax, tuples, d2h = 0.0, 0.0, 0, 0, 0, 0
     for _ in range(args.steps):
         t0 = time.perf_counter()
-        m = L.compose_frozen_shortest_path_batch_multi(fst, data, offsets, devices=devices, chunks_per_device=args.chunks_per_device, copy=False)
+        m = L.compose_frozen_shortest_path_batch_multi(fst, data, offsets, devices=devices, chunks_per_device=args.chunks_per_device, copy=False, flags=rflags)
         wall += time.perf_counter() - t0
         dev_ms += m.device_ms; launches += m.launches; relax = m.total_relax; tuples = m.total_tuples; d2h = m.d2h_bytes
     for s in samplers:
@@ -482,6 +485,7 @@ def run_strong(args):
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": dict(workload_config(args, total // args.gpus, 1 << 40), total_strings=total, chunks=len(m.chunk_first) - 1,
                        entry="fst_compose_frozen_shortest_path_batch_multi (one process, one host thread per GPU, no collective)",
+                       result=("output strings + statuses + path lengths (FST_B200_RESULT_NO_PATHS)" if args.bytes_only else "full paths + output strings"),
                        distinct_strings=min(total, args.distinct) if args.workload == "wetext" else len(np.unique(np.diff(offsets.astype(np.int64))))),
         "composed_arcs_per_sec": value * relax_ps,
         "work_per_string": {"path_arcs": path_arcs, "tuples_run": tuples_ps, "relax_run": relax_ps, "mean_len": nbytes / total,
@@ -613,13 +617,15 @@ def main():
         d2h = 0
         e2e_dev_ms = 0.0
         for _ in range(args.steps):
-            r = L.compose_frozen_shortest_path_batch(fst, hb, ho)
+            # the C-ABI call with host buffers: H2D of the strings, search, D2H of the whole result into pinned host
+            # memory, and the release of that result (copy=False: no numpy copies of the result inside the timed region)
+            r = L.compose_frozen_shortest_path_batch(fst, hb, ho, copy=False)
             e2e_dev_ms += r.device_ms
-            d2h = (r.status.nbytes + r.path_offsets.nbytes + r.ilabels.nbytes + r.olabels.nbytes + r.weights.nbytes +
-                   r.final_weights.nbytes + r.n_tuples.nbytes + r.out_offsets.nbytes + r.out_bytes.nbytes)
+            d2h = r.d2h_bytes
         torch.cuda.synchronize()
         e2e_ms = (time.perf_counter() - t0) * 1e3
-        # the host-buffer result is the device-resident one
+        # the host-buffer result is the device-resident one (one more call, untimed, with copies)
+        r = L.compose_frozen_shortest_path_batch(fst, hb, ho)
         hi = int(poff[-1])
         assert np.array_equal(r.status, st) and np.array_equal(r.path_offsets.astype(np.int64), poff)
         assert np.array_equal(r.ilabels, d_il[:hi].cpu().numpy().astype(np.uint32)) and np.array_equal(r.olabels, d_ol[:hi].cpu().numpy().astype(np.uint32))

@@ -153,6 +153,13 @@ typedef struct {
  * device / kernel failure.  *out is set to NULL on error. */
 FstError fst_compose_frozen_shortest_path_batch(FstHandle b, const uint8_t* bytes, const uint64_t* offsets,
                                                 uint32_t n_strings, FstB200BatchResult** out);
+/* The same with result flags.  FST_B200_RESULT_NO_PATHS: the caller only wants what fst_print_output_string gives
+ * (out_offsets / out_bytes) plus status, final weight, path LENGTHS (path_offsets) and counters; the per-arc arrays
+ * (ilabels / olabels / weights, 16 bytes per path arc — most of the D2H of a tagger batch) are not copied back and
+ * the three pointers are NULL.  Unknown flags: FST_INVALID_ARG. */
+enum { FST_B200_RESULT_NO_PATHS = 1 };
+FstError fst_compose_frozen_shortest_path_batch_ex(FstHandle b, const uint8_t* bytes, const uint64_t* offsets,
+                                                   uint32_t n_strings, uint32_t flags, FstB200BatchResult** out);
 void fst_b200_batch_free(FstB200BatchResult* r);
 
 /* Two-stage pipeline on the device (the reference's ITN flow README.md:177-189: per utterance
@@ -172,7 +179,8 @@ FstError fst_compose_frozen_shortest_path_pipeline(FstHandle first, FstHandle se
  * (own stream; async D2H into the chunk's pinned result).  No collective: strings are independent.  The result lists
  * the chunks IN INPUT ORDER: chunk k holds strings [chunk_first[k], chunk_first[k+1]) as an ordinary batch result
  * (string i of the batch = string i - chunk_first[k] of its chunk), so nothing is copied a second time.
- * `devices` == NULL or n_devices == 0: every visible device.  chunks_per_device == 0: default (2).  Errors as for the
+ * `devices` == NULL or n_devices == 0: every visible device.  chunks_per_device == 0: default (2).  `flags` as for
+ * fst_compose_frozen_shortest_path_batch_ex.  Errors as for the
  * batch entry; an unknown or repeated device is FST_INVALID_ARG.  Per-string results do not depend on the device
  * list (byte-identical for 1, 2, 4, 8 GPUs). */
 typedef struct {
@@ -189,7 +197,7 @@ typedef struct {
 } FstB200MultiResult;
 FstError fst_compose_frozen_shortest_path_batch_multi(FstHandle b, const uint8_t* bytes, const uint64_t* offsets,
                                                       uint32_t n_strings, const int32_t* devices, uint32_t n_devices,
-                                                      uint32_t chunks_per_device, FstB200MultiResult** out);
+                                                      uint32_t chunks_per_device, uint32_t flags, FstB200MultiResult** out);
 void fst_b200_multi_free(FstB200MultiResult* r);
 
 /* Eager lattices on the device: for every string i the result of

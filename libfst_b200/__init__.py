@@ -21,6 +21,7 @@ FST_NO_STATE = 0xFFFFFFFF
 FST_EPSILON = 0
 FST_INVALID_HANDLE = 0xFFFFFFFFFFFFFFFF
 PATH, NO_PATH, CYCLE, TOO_LARGE, INTERNAL, NOT_BYTES = 0, 1, 2, 3, 4, 5
+RESULT_NO_PATHS = 1
 
 
 class FstArc(C.Structure):
@@ -97,7 +98,9 @@ EXPORTS = {
                                                                    C.POINTER(C.POINTER(_BatchResult))]),
     "fst_b200_last_path_required": (C.c_uint64, []),
     "fst_compose_frozen_shortest_path_batch_multi": (C.c_int, [C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
-                                                               C.c_uint32, C.POINTER(C.POINTER(_MultiResult))]),
+                                                               C.c_uint32, C.c_uint32, C.POINTER(C.POINTER(_MultiResult))]),
+    "fst_compose_frozen_shortest_path_batch_ex": (C.c_int, [C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
+                                                            C.POINTER(C.POINTER(_BatchResult))]),
     "fst_b200_multi_free": (None, [C.POINTER(_MultiResult)]),
     "fst_b200_batch_free": (None, [C.POINTER(_BatchResult)]),
     "fst_b200_compose_frozen_lattice_batch": (C.c_int, [C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32,
@@ -329,6 +332,20 @@ class BatchResult:
         return t + float(self.final_weights[i])
 
 
+@dataclass
+class BatchSummary:
+    """What a batched call returned, without copying its arrays (compose_frozen_shortest_path_batch(copy=False))."""
+    n_strings: int
+    path_arcs: int
+    out_bytes: int
+    d2h_bytes: int        # bytes of the pinned host result the call filled
+    device_ms: float
+    total_tuples: int
+    total_relax: int
+    launches: int
+    passes: int
+
+
 def pack_strings(strings):
     """list[bytes] -> (uint8 data, uint64 offsets[n+1])."""
     lens = np.fromiter((len(s) for s in strings), np.uint64, len(strings))
@@ -349,14 +366,16 @@ def compose_frozen_then_shortest_path_batch(b: Fst, data: np.ndarray, offsets: n
 
 
 def compose_frozen_shortest_path_batch(b: Fst, data: np.ndarray, offsets: np.ndarray, copy: bool = True, second: Fst = None,
-                                       eager: bool = False) -> BatchResult:
+                                       eager: bool = False, flags: int = 0) -> BatchResult:
     """fst_compose_frozen_shortest_path_batch over host buffers (`second`: the two-stage pipeline entry)."""
     data = np.ascontiguousarray(data, np.uint8)
     offsets = np.ascontiguousarray(offsets, np.uint64)
     n = len(offsets) - 1
     keep = data if data.size else np.zeros(1, np.uint8)
     out = C.POINTER(_BatchResult)()
-    if eager:
+    if flags:
+        rc = lib().fst_compose_frozen_shortest_path_batch_ex(b.h, keep.ctypes.data, offsets.ctypes.data, n, flags, C.byref(out))
+    elif eager:
         rc = lib().fst_b200_compose_frozen_then_shortest_path_batch(b.h, keep.ctypes.data, offsets.ctypes.data, n, C.byref(out))
     elif second is None:
         rc = lib().fst_compose_frozen_shortest_path_batch(b.h, keep.ctypes.data, offsets.ctypes.data, n, C.byref(out))
@@ -365,6 +384,14 @@ def compose_frozen_shortest_path_batch(b: Fst, data: np.ndarray, offsets: np.nda
     if rc != FST_OK:
         raise RuntimeError(f"fst_compose_frozen_shortest_path_batch failed: FstError {rc}")
     try:
+        if not copy:
+            # summary only (bench: the timed region is the C-ABI call, not numpy copies of its pinned result)
+            r = out.contents
+            pt, ot = (int(r.path_offsets[n]), int(r.out_offsets[n])) if n else (0, 0)
+            if not r.ilabels:
+                pt = 0
+            return BatchSummary(n, pt, ot, n * (4 + 8 + 4) + 2 * (n + 1) * 8 + pt * 16 + ot, r.device_ms, r.total_tuples, r.total_relax,
+                                r.launches, r.passes)
         return _copy_batch_result(out.contents, n)
     finally:
         lib().fst_b200_batch_free(out)
@@ -378,6 +405,8 @@ def _copy_batch_result(r, n) -> BatchResult:
     poff = arr(r.path_offsets, n + 1, np.uint64)
     ooff = arr(r.out_offsets, n + 1, np.uint64)
     total, ototal = int(poff[-1]), int(ooff[-1])
+    if not r.ilabels:          # FST_B200_RESULT_NO_PATHS: lengths only
+        total = 0
     return BatchResult(arr(r.status, n, np.int32), poff, arr(r.ilabels, total, np.uint32), arr(r.olabels, total, np.uint32),
                        arr(r.weights, total, np.float64), arr(r.final_weights, n, np.float64), arr(r.n_tuples, n, np.uint32),
                        ooff, arr(r.out_bytes, ototal, np.uint8), r.device_ms, r.total_tuples, r.total_relax, r.launches, r.passes)
@@ -413,7 +442,7 @@ class MultiResult:
 
 
 def compose_frozen_shortest_path_batch_multi(b: Fst, data: np.ndarray, offsets: np.ndarray, devices=None, chunks_per_device: int = 0,
-                                             copy: bool = True):
+                                             copy: bool = True, flags: int = 0):
     """fst_compose_frozen_shortest_path_batch_multi.  copy=False returns only the summary (counters, chunk layout) and frees
     the native result at once (bench: the timed region must not include numpy copies)."""
     data = np.ascontiguousarray(data, np.uint8)
@@ -424,7 +453,7 @@ def compose_frozen_shortest_path_batch_multi(b: Fst, data: np.ndarray, offsets: 
     out = C.POINTER(_MultiResult)()
     rc = lib().fst_compose_frozen_shortest_path_batch_multi(b.h, keep.ctypes.data, offsets.ctypes.data, n,
                                                             None if dev is None else dev.ctypes.data, 0 if dev is None else len(dev),
-                                                            chunks_per_device, C.byref(out))
+                                                            chunks_per_device, flags, C.byref(out))
     if rc != FST_OK:
         raise RuntimeError(f"fst_compose_frozen_shortest_path_batch_multi failed: FstError {rc}")
     r = out.contents
@@ -440,7 +469,7 @@ def compose_frozen_shortest_path_batch_multi(b: Fst, data: np.ndarray, offsets: 
             if copy:
                 chunks.append(_copy_batch_result(c, cn))
             else:
-                pt, ot = int(c.path_offsets[cn]), int(c.out_offsets[cn])
+                pt, ot = (int(c.path_offsets[cn]) if c.ilabels else 0), int(c.out_offsets[cn])
                 d2h += cn * (4 + 8 + 4) + 2 * (cn + 1) * 8 + pt * 16 + ot
         m = MultiResult(first, cdev, chunks, r.n_devices, r.wall_ms, r.device_ms, r.total_tuples, r.total_relax, r.launches)
         m.d2h_bytes = d2h

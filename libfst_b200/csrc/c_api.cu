@@ -479,7 +479,7 @@ static int32_t map_status(int32_t s) {
 
 // Host-buffer batch against one transducer (b2 == FST_INVALID_HANDLE) or the two-stage pipeline b then b2.
 static FstError host_batch(FstHandle b, FstHandle b2, const uint8_t* bytes, const uint64_t* offsets,
-                           uint32_t n_strings, FstB200BatchResult** out, int semantics = -1) {
+                           uint32_t n_strings, FstB200BatchResult** out, int semantics = -1, uint32_t flags = 0) {
   if (!out) return FST_INVALID_ARG;
   *out = nullptr;
   if (!offsets || (!bytes && n_strings && offsets[n_strings] > 0)) return FST_INVALID_ARG;
@@ -570,7 +570,9 @@ static FstError host_batch(FstHandle b, FstHandle b2, const uint8_t* bytes, cons
   t_last = bc;
   // assemble the pinned host result
   NvtxRange nvtx_d2h("fstb200 result D2H");
-  const uint64_t total = bc.path_total;
+  // FST_B200_RESULT_NO_PATHS: the caller only wants the output strings — the per-arc arrays stay on the device
+  const bool want_paths = !(flags & FST_B200_RESULT_NO_PATHS);
+  const uint64_t total = want_paths ? bc.path_total : 0;
   uint64_t out_total = 0;
   if (n) cudaMemcpy(&out_total, d_ooff + n, 8, cudaMemcpyDeviceToHost);
   auto al = [](size_t x) { return (x + 63) & ~(size_t)63; };
@@ -602,9 +604,9 @@ static FstError host_batch(FstHandle b, FstHandle b2, const uint8_t* bytes, cons
   r->pub.n_strings = n;
   r->pub.status = hs;
   r->pub.path_offsets = reinterpret_cast<uint64_t*>(hb + o_poff);
-  r->pub.ilabels = reinterpret_cast<uint32_t*>(hb + o_il);
-  r->pub.olabels = reinterpret_cast<uint32_t*>(hb + o_ol);
-  r->pub.weights = reinterpret_cast<double*>(hb + o_w);
+  r->pub.ilabels = want_paths ? reinterpret_cast<uint32_t*>(hb + o_il) : nullptr;
+  r->pub.olabels = want_paths ? reinterpret_cast<uint32_t*>(hb + o_ol) : nullptr;
+  r->pub.weights = want_paths ? reinterpret_cast<double*>(hb + o_w) : nullptr;
   r->pub.final_weights = reinterpret_cast<double*>(hb + o_fin);
   r->pub.n_tuples = reinterpret_cast<uint32_t*>(hb + o_nt);
   r->pub.out_offsets = reinterpret_cast<uint64_t*>(hb + o_ooff);
@@ -621,6 +623,11 @@ static FstError host_batch(FstHandle b, FstHandle b2, const uint8_t* bytes, cons
 FstError fst_compose_frozen_shortest_path_batch(FstHandle b, const uint8_t* bytes, const uint64_t* offsets,
                                                 uint32_t n_strings, FstB200BatchResult** out) {
   return host_batch(b, FST_INVALID_HANDLE, bytes, offsets, n_strings, out);
+}
+FstError fst_compose_frozen_shortest_path_batch_ex(FstHandle b, const uint8_t* bytes, const uint64_t* offsets,
+                                                   uint32_t n_strings, uint32_t flags, FstB200BatchResult** out) {
+  if (flags & ~(uint32_t)FST_B200_RESULT_NO_PATHS) { if (out) *out = nullptr; return FST_INVALID_ARG; }
+  return host_batch(b, FST_INVALID_HANDLE, bytes, offsets, n_strings, out, -1, flags);
 }
 
 // Eager pair per call (BASELINE config 5): fst_compose_frozen then fst_shortest_path(., 1) of every string, as its own
@@ -651,9 +658,10 @@ struct MultiResultImpl {
 
 FstError fst_compose_frozen_shortest_path_batch_multi(FstHandle b, const uint8_t* bytes, const uint64_t* offsets, uint32_t n_strings,
                                                       const int32_t* devices, uint32_t n_devices, uint32_t chunks_per_device,
-                                                      FstB200MultiResult** out) {
+                                                      uint32_t flags, FstB200MultiResult** out) {
   if (!out) return FST_INVALID_ARG;
   *out = nullptr;
+  if (flags & ~(uint32_t)FST_B200_RESULT_NO_PATHS) return FST_INVALID_ARG;
   if (!offsets || (!bytes && n_strings && offsets[n_strings] > 0)) return FST_INVALID_ARG;
   for (uint32_t i = 0; i < n_strings; i++) if (offsets[i + 1] < offsets[i]) return FST_INVALID_ARG;
   int visible = 0;
@@ -711,7 +719,7 @@ FstError fst_compose_frozen_shortest_path_batch_multi(FstHandle b, const uint8_t
       if (k >= n_chunks || first_err.load() != FST_OK) break;
       const uint32_t lo = (uint32_t)r->first[k], hi = (uint32_t)r->first[k + 1];
       FstB200BatchResult* res = nullptr;
-      const FstError e = host_batch(b, FST_INVALID_HANDLE, bytes, offsets + lo, hi - lo, &res);
+      const FstError e = host_batch(b, FST_INVALID_HANDLE, bytes, offsets + lo, hi - lo, &res, -1, flags);
       if (e != FST_OK) { int expect = FST_OK; first_err.compare_exchange_strong(expect, (int)e); break; }
       r->chunks[k] = res; r->device[k] = devs[w];
       dev_ms[w] += res->device_ms;

@@ -101,3 +101,25 @@ def test_multi_gpu_epsilon_dense_sample(L, O, gpu):
         assert np.array_equal(il, p.ilabels) and np.array_equal(ol, p.olabels)
         assert np.array_equal(w.view(np.uint64), p.weights.view(np.uint64))
     assert (flat.status == L.PATH).all() and len(set(m.chunk_device.tolist())) == min(L.device_count(), len(m.chunks))
+
+
+def test_result_without_path_arrays(L, O, gpu):
+    """FST_B200_RESULT_NO_PATHS: output strings, statuses, final weights and path LENGTHS as usual, no per-arc arrays."""
+    rng = random.Random(12)
+    spec = random_rhs(rng, max_states=7, nlab=3)
+    fprod, forc, _ = frozen_pair(L, O, spec)
+    strings = [random_string(rng, nlab=3, max_len=12) for _ in range(500)]
+    data, offsets = L.pack_strings(strings)
+    full = L.compose_frozen_shortest_path_batch(fprod, data, offsets)
+    lean = L.compose_frozen_shortest_path_batch(fprod, data, offsets, flags=L.RESULT_NO_PATHS)
+    assert len(lean.ilabels) == 0 and len(lean.weights) == 0
+    assert np.array_equal(lean.status, full.status) and np.array_equal(lean.path_offsets, full.path_offsets)
+    assert np.array_equal(lean.out_offsets, full.out_offsets) and np.array_equal(lean.out_bytes, full.out_bytes)
+    assert np.array_equal(lean.final_weights.view(np.uint64), full.final_weights.view(np.uint64))
+    m = L.compose_frozen_shortest_path_batch_multi(fprod, data, offsets, chunks_per_device=3, flags=L.RESULT_NO_PATHS)
+    for c, lo in zip(m.chunks, m.chunk_first[:-1]):
+        lo = int(lo)
+        for i in range(len(c.status)):
+            assert c.status[i] == full.status[lo + i] and c.output(i) == full.output(lo + i)
+    with pytest.raises(RuntimeError):
+        L.compose_frozen_shortest_path_batch(fprod, data, offsets, flags=6)
