@@ -280,9 +280,6 @@ __device__ FAST_POP_FN void fast_pop_loop(FastCold& f) {
   asm volatile("" : "+r"(lane), "+r"(gbase), "+r"(gmask), "+r"(ltmw), "+r"(win_s));
   const uint4* const slab_lane = F.islab + lane;
   const uint32_t smask = (1u << p.key_sbits) - 1u;
-#ifdef FSTB_FAST_KEYFWD
-  uint32_t fwd_id = 0xFFFFFFFFu, fwd_key = 0u;
-#endif
   for (;;) {
     const uint32_t w = fast_lds(win_s + lane * 4u);
     const unsigned gb = (__ballot_sync(FULL, w != 0) >> gbase) & 0xFFu;
@@ -296,19 +293,7 @@ __device__ FAST_POP_FN void fast_pop_loop(FastCold& f) {
     uint32_t cur_id = running ? (wline << 8) + ((uint32_t)src << 5) + bit : 0u;
     if (EAGER && bfsm) cur_id = cursor++;
     if ((int)lane == src) fast_red_and(win_s + (uint32_t)src * 4u, ~(1u << bit));
-#ifdef FSTB_FAST_KEYFWD
-    // key forwarding: the popped tuple is usually one that the last step of this group made ready (a chain): the lane
-    // that relaxed it still holds its key.  The id -> key load is skipped when every group of the warp is served.
-    uint32_t key;
-    {
-      const unsigned fm = __ballot_sync(FULL, fwd_id == cur_id) & gmask;
-      if (__all_sync(FULL, fm != 0u || !running)) key = __shfl_sync(FULL, fwd_key, __ffs(fm | 0x80000000u) - 1);
-      else { key = key_of[cur_id]; if (fm) key = __shfl_sync(gmask, fwd_key, __ffs(fm) - 1); }
-      if (!running) key = key_of[cur_id];
-    }
-#else
     const uint32_t key = key_of[cur_id];
-#endif
     const uint32_t P = key >> p.key_sbits, s2 = (key & smask) >> 1;
     const uint4 sa = __ldg(slab_lane + (size_t)s2 * kWaveSlots);    // {ilabel, next << 1 | eps, weight << 12, arcs folded}
     // dense index (SearchParams::pos_h): sa.y = next << 1 | epsilon; the per-pop parts are uniform over the group
@@ -344,9 +329,6 @@ __device__ FAST_POP_FN void fast_pop_loop(FastCold& f) {
     }
     const uint32_t tkey = ((is_match ? P + 1u : P) << p.key_sbits) | sa.y;
     if (is_new) key_of[my_id] = tkey;
-#ifdef FSTB_FAST_KEYFWD
-    fwd_id = (lowered && sa.z == 0u) ? my_id : 0xFFFFFFFFu; fwd_key = tkey;
-#endif
     n_tuples += __popc(nv & gmask);
     // queue: ready set at the current level, else the future set
     const bool fut = lowered && sa.z != 0u;
