@@ -526,6 +526,9 @@ static FstError host_batch(FstHandle b, FstHandle b2, const uint8_t* bytes, cons
   for (int attempt = 0;; attempt++) {
     if (en->ensure_io(n, nbytes, path_cap) != cudaSuccess) { cudaGetLastError(); return FST_OOM; }
     const Engine::IoBuffers& io = en->io();
+    // the flat path arrays are grow-only: use all of them (a transducer that inserts output — a tagger — needs several
+    // arcs per input byte; sizing every call from the input alone would run its first attempt in vain each time)
+    path_cap = std::max<uint64_t>(path_cap, io.cap_path);
     d_bytes = io.bytes; d_offsets = io.offsets; d_status = io.status; d_poff = io.path_offsets; d_il = io.il; d_ol = io.ol; d_w = io.w;
     d_fin = io.final_w; d_nt = io.n_tuples; d_ooff = io.out_offsets; d_obytes = io.out_bytes;
     {
@@ -556,6 +559,7 @@ static FstError host_batch(FstHandle b, FstHandle b2, const uint8_t* bytes, cons
     for (int attempt = 0;; attempt++) {
       if (en->ensure_io(n, 0, path_cap, 1) != cudaSuccess) { cudaGetLastError(); return FST_OOM; }
       const Engine::IoBuffers& io = en->io(1);
+      path_cap = std::max<uint64_t>(path_cap, io.cap_path);
       d_status = io.status; d_poff = io.path_offsets; d_il = io.il; d_ol = io.ol; d_w = io.w;
       d_fin = io.final_w; d_nt = io.n_tuples; d_ooff = io.out_offsets; d_obytes = io.out_bytes;
       err = en->run_batch(img2, d_in2, d_off2, n, max_len2, d_status, d_poff, d_il, d_ol, d_w, d_fin, d_nt, path_cap, d_ooff, d_obytes, path_cap, stream, &bc, d_status1,
