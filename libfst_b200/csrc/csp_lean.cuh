@@ -569,7 +569,9 @@ __device__ __forceinline__ void lean_relax(const SearchParams& p, const Group<G>
       const uint32_t rank = in_first ? __popc(newmask & first & lt) : (__popc(newmask & first) + __popc(newmask & ~first & lt));
       my_id = st.n_tuples + rank;   // discovery order == reference expansion order (:80-87)
       lean_keyof_store<DENSE>(p, c, my_id, P, SF);
-      if (untouched) pos = lean_claim<DENSE>(p, c, P, SF, pos);
+      // hash table: the empty slot the probe found is claimed with a CAS only if another lane of the group inserts in
+      // this step too (only this group writes to this arena; a lone insert cannot race: lean_store writes the key)
+      if (untouched && (DENSE || ((EAGER && bfs) ? n_unt : n_new) > 1u)) pos = lean_claim<DENSE>(p, c, P, SF, pos);
     }
     if (bfs) {
       // eager semantics: the first tight relaxer in FIFO order is the smallest-numbered tight predecessor
