@@ -398,8 +398,8 @@ def single_call_latency(L, oracle, fst, f, args, iters=20, warm=3):
     il, ol, w, fw = r.chain()
     assert np.array_equal(il, p.ilabels) and np.array_equal(ol, p.olabels)
     return {"gpu_avg_ns": gpu_ns, "cpu_port_avg_ns": cpu_ns, "iters": iters, "warmup": warm,
-            "note": "one string per call through fst_compose_frozen_shortest_path (general-left-operand warp kernel, one warp); "
-                    "CPU = C++ port of the reference, one core; the batch entry is the throughput path"}
+            "note": "one string per call through fst_compose_frozen_shortest_path (a compiled string runs as a one-string batch: "
+                    "one 8-lane group of the lean / fast kernel); CPU = C++ port of the reference, one core; the batch entry is the throughput path"}
 
 
 def run_matrix(args):

@@ -393,6 +393,30 @@ static int32_t print_tape(FstMutableHandle handle, bool output, uint8_t* buf, ui
 int32_t fst_print_string(FstMutableHandle handle, uint8_t* buf, uint32_t buf_len) { return print_tape(handle, false, buf, buf_len); }
 int32_t fst_print_output_string(FstMutableHandle handle, uint8_t* buf, uint32_t buf_len) { return print_tape(handle, true, buf, buf_len); }
 
+// Is `a` exactly what fst_compile_string builds (src/string.zig:24-50 with input == output: states 0..n, state i has
+// the one arc (b+1 : b+1 / One -> i+1), only state n is final with weight One)?  Then the single call is the batched
+// search of one byte string (the lean / fast kernels instead of the general-left-operand warp kernel: same search,
+// ~4x lower latency).
+static bool as_byte_string(const HostMutable& a, std::vector<uint8_t>* bytes) {
+  const uint32_t ns = a.num_states();
+  if (ns == 0 || a.start != 0) return false;
+  const uint32_t n = ns - 1;
+  auto bits = [](double x) { unsigned long long b; std::memcpy(&b, &x, 8); return b; };
+  const unsigned long long inf_bits = bits(std::numeric_limits<double>::infinity());
+  bytes->resize(n);
+  for (uint32_t i = 0; i < n; i++) {
+    if (a.arcs[i].size() != 1 || bits(a.finals[i]) != inf_bits) return false;
+    const HostArc& x = a.arcs[i][0];
+    if (x.ilabel != x.olabel || x.ilabel == 0 || x.ilabel > 256 || x.nextstate != i + 1 || bits(x.weight) != 0ull) return false;
+    (*bytes)[i] = (uint8_t)(x.ilabel - 1);
+  }
+  return a.arcs[n].empty() && bits(a.finals[n]) == 0ull;
+}
+
+static FstError host_batch(FstHandle b, FstHandle b2, const uint8_t* bytes, const uint64_t* offsets,
+                           uint32_t n_strings, FstB200BatchResult** out, int semantics = -1, uint32_t flags = 0);
+void fst_b200_batch_free(FstB200BatchResult* r);
+
 // ── THE HOT PATH, single problem (src/c-api.zig:744-811) ──
 FstMutableHandle fst_compose_frozen_shortest_path(FstMutableHandle a_handle, FstHandle b_handle, uint32_t n) {
   const bool trace = trace_enabled();
@@ -439,7 +463,22 @@ FstMutableHandle fst_compose_frozen_shortest_path(FstMutableHandle a_handle, Fst
     if (!img) return fail();
     int32_t status = kStNoPath; double fw = 0;
     std::vector<uint32_t> il, ol; std::vector<double> w;
-    {
+    std::vector<uint8_t> str;
+    if (as_byte_string(a, &str)) {
+      // a compiled string: one-string batch (always the lazy semantics of this entry point)
+      const uint64_t off[2] = {0, str.size()};
+      const uint8_t dummy = 0;
+      FstB200BatchResult* res = nullptr;
+      if (host_batch(b_handle, FST_INVALID_HANDLE, str.empty() ? &dummy : str.data(), off, 1, &res, 0, 0) != FST_OK) return fail();
+      const int32_t s1 = res->status[0];
+      status = (s1 == FST_B200_PATH || s1 == FST_B200_NOT_BYTES) ? kStPath : (s1 == FST_B200_NO_PATH ? kStNoPath : kStInternal);
+      if (status == kStPath) {
+        const uint64_t lo = res->path_offsets[0], hi = res->path_offsets[1];
+        il.assign(res->ilabels + lo, res->ilabels + hi); ol.assign(res->olabels + lo, res->olabels + hi); w.assign(res->weights + lo, res->weights + hi);
+        fw = res->final_weights[0];
+      }
+      fst_b200_batch_free(res);
+    } else {
       std::lock_guard<std::mutex> lk(en->mu);
       BatchCounters bc;
       err = en->run_general(img, a, lhs_neg, &status, &il, &ol, &w, &fw, &bc);
@@ -479,7 +518,7 @@ static int32_t map_status(int32_t s) {
 
 // Host-buffer batch against one transducer (b2 == FST_INVALID_HANDLE) or the two-stage pipeline b then b2.
 static FstError host_batch(FstHandle b, FstHandle b2, const uint8_t* bytes, const uint64_t* offsets,
-                           uint32_t n_strings, FstB200BatchResult** out, int semantics = -1, uint32_t flags = 0) {
+                           uint32_t n_strings, FstB200BatchResult** out, int semantics, uint32_t flags) {
   if (!out) return FST_INVALID_ARG;
   *out = nullptr;
   if (!offsets || (!bytes && n_strings && offsets[n_strings] > 0)) return FST_INVALID_ARG;
