@@ -167,6 +167,17 @@ def test_search_calls_fail_loudly_without_a_gpu(L, capfd):
     assert e is not None and e.num_states() == 0
     out = C.POINTER(L._BatchResult)()
     assert L.lib().fst_compose_frozen_shortest_path_batch(L.FST_INVALID_HANDLE, None, None, 0, C.byref(out)) == L.FST_INVALID_ARG
+    # the other batched entries: no device -> FST_INVALID_STATE (3), loudly; bad flags -> FST_INVALID_ARG (2) first
+    with pytest.raises(RuntimeError, match="FstError 3"):
+        L.compose_frozen_then_shortest_path_batch(f, data, off)
+    with pytest.raises(RuntimeError, match="FstError 3"):
+        L.compose_frozen_shortest_path_batch_multi(f, data, off)
+    assert "no CPU fallback" in capfd.readouterr().err
+    with pytest.raises(RuntimeError, match="FstError 2"):
+        L.compose_frozen_shortest_path_batch(f, data, off, flags=8)
+    with pytest.raises(RuntimeError, match="FstError 2"):
+        L.compose_frozen_shortest_path_batch_multi(f, data, off, flags=8)
+    assert L.lib().fst_b200_last_path_required() == 0
 
 
 def test_freed_frozen_handle_is_invalid(L, tmp_path):
