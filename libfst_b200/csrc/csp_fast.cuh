@@ -3,8 +3,9 @@
 // advance, the back-track and the arena clean-up are the functions of that file); what is new is the STEP:
 //
 //   configuration   8 lanes per string reading the INTEGER leader slab (`islab`), dense table of compact 8-byte
-//                   records (every weight of the transducer is an integer in 0..4095), lazy semantics
-//                   (compose-shortest-path.zig:26-401).  Everything else stays with csp_batch_lean_kernel.
+//                   records (every weight of the transducer is an integer in 0..4095); lazy semantics
+//                   (compose-shortest-path.zig:26-401) and, as a second instantiation, the eager pair
+//                   (compose.zig:29-198 + shortest-path.zig:18-139).  Everything else stays with csp_batch_lean_kernel.
 //   integer relax   the compact record is  dist:20 | prev:22 | id:22  (most significant first).  With
 //                   cand = (new dist, popped id) in the same position, the reference's rule (:109-126)
 //                       take  <=>  new < old  ||  (new == old && (no back-pointer || popped id < prev))
@@ -12,11 +13,15 @@
 //                   taken; "no back-pointer" is the largest prev), "strictly lowered" (:109-114, :137-142) is
 //                   (cand | low 12 bits) < high word, and the new record is cand with the tuple's id below it.
 //                   The slab carries the weight pre-shifted to the distance field: no f64 in the loop.
-//   service split   the loop body is straight-line code that every lane of the warp executes (warp-wide
-//                   votes, no per-group branches except the rare ones: final state, a state wider than the
-//                   slab, a second distance level).  Anything else a string needs — next window line, next
-//                   level, evicting the window below a new smaller id, the end of the string, the next string
-//                   — raises its group's service flag; a warp with a flag up runs one service iteration.
+//   service split   the POP LOOP (fast_pop_loop) is an out-of-line leaf function of straight-line code that every
+//                   lane of the warp executes: warp-wide votes, no calls, its own register allocation.  It
+//                   returns when a group needs SERVICE (next window line, next level, evicting the window below
+//                   a new smaller id, the end of the string, the next string: fast_service) or when a step has a
+//                   RARE TAIL (final check at the end of the string, an id below the window, a push into the
+//                   radix heap once it exists, a state wider than the slab: fast_rare); the kernel runs that for
+//                   the groups that asked and re-enters the loop.  The hot values travel through a struct in local
+//                   memory (FastCold), the launch parameters through __constant__ memory (a leaf reads
+//                   constant-bank operands for free).
 //   idle groups     a group without a string reads the dummy state row S of the slab (no record matches), so
 //                   the hot path needs no "is my group alive" branches.
 //
